@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — SE(3)-ICP registrations/s on KITTI-size clouds (BASELINE.json metric, configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--pairs-per-gpu P]
+
+A "step" is one pass of the registration hot path (se3_gicp, benchmark_kitti.cpp:133-148 parameters)
+over one batch of synthetic KITTI-like scan pairs.  Weak scaling: every GPU owns `pairs_per_gpu`
+independent pairs (32 -> 256 pairs at 8 GPUs, the named configuration); no data-path collective.
+
+  value     whole-job registrations/s with the scans already resident in HBM
+            (se3icp_run_batch_device), CUDA-event timed, max over ranks
+  e2e       same through the host-buffer C-ABI call a reference user makes (se3icp_run_batch from
+            pinned host memory: H2D of both scans + D2H of the 4x4 result inside the timed region)
+  roofline  the dominant kernel (SE(3) 12-D nearest-neighbour sweep) against the measured HBM peak:
+            algorithmic bytes 48 N + 48 M + 8 N per launch / live CUDA-event time
+  cpu_baseline  the CPU oracle (a port: the reference needs Open3D/PCL/Eigen, absent here) timed on
+            the host cores on one pair of the same workload
+  --impl reference   times only that CPU path (rank 0), same metric/config
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+import workloads as W  # noqa: E402
+
+METRIC = "SE(3)-ICP registrations/s @KITTI-size clouds (se3_gicp)"
+UNIT = "registrations/s"
+UNIQUE_PAIRS = 8  # distinct synthetic scenes per GPU, cycled to pairs_per_gpu
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=32)
+    ap.add_argument("--contexts", type=int, default=4, help="concurrent registration contexts (streams) per GPU")
+    ap.add_argument("--n-az", type=int, default=1900, help="azimuth steps of the synthetic 64-ring scanner")
+    return ap.parse_args()
+
+
+def kitti_params(mod):
+    return mod.default_params(variant="gicp", entry=mod.RUN_SE3_ICP, **W.KITTI_PARAMS)
+
+
+def make_pairs(rank, n_az):
+    return [W.lidar_pair(seed=rank * UNIQUE_PAIRS + i, n_az=n_az) for i in range(UNIQUE_PAIRS)]
+
+
+def config_dict(args, pairs, n_gpus):
+    n_src = int(np.mean([len(p[0]) for p in pairs]))
+    n_tgt = int(np.mean([len(p[1]) for p in pairs]))
+    return {
+        "workload": "KITTI-like synthetic LiDAR scan pairs (64 rings x %d azimuth steps, ~%dk/%dk points), se3_gicp, "
+                    "overlap 0.7, mse 1e-7, switch 5e-7, max_se3 10, kNN 90, alpha 3 (BASELINE.json configs[2])"
+                    % (args.n_az, n_src // 1000, n_tgt // 1000),
+        "pairs_per_gpu": args.pairs_per_gpu, "global_pairs": args.pairs_per_gpu * n_gpus,
+        "unique_pairs_per_gpu": UNIQUE_PAIRS, "points_src": n_src, "points_tgt": n_tgt,
+        "parallelism": "independent pairs sharded over %d GPU(s), no collective" % n_gpus,
+        "l2": "each step streams %d distinct scans (> L2) through the pipeline; no cached outputs" % (2 * UNIQUE_PAIRS),
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(orc, pair):
+    src, tgt, _ = pair
+    t0 = time.perf_counter()
+    T, st, _ = orc.run(src, tgt, kitti_params(orc))
+    return time.perf_counter() - t0, T, st
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port) on all host threads, one pair per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc = graft.load_oracle()
+    pairs = [W.lidar_pair(seed=i, n_az=args.n_az) for i in range(min(UNIQUE_PAIRS, args.steps + args.warmup))]
+    for w in range(args.warmup):
+        cpu_reference_step(orc, pairs[w % len(pairs)])
+    t = 0.0
+    for s in range(args.steps):
+        dt, _, _ = cpu_reference_step(orc, pairs[(args.warmup + s) % len(pairs)])
+        t += dt
+    value = args.steps / t
+    sample = "%d full-size pairs (1 per step), %d OpenMP threads" % (args.steps, orc.num_threads())
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, pairs, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be built offline (needs Open3D 0.19, PCL 1.14, Eigen); this is the oracle port",
+    }))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = graft.load_package()
+    capi = pkg.capi
+    params = kitti_params(capi)
+    pairs = make_pairs(rank, args.n_az)
+    P = args.pairs_per_gpu
+    order = [i % UNIQUE_PAIRS for i in range(P)]
+
+    # resident inputs (value) and pinned host inputs (e2e)
+    dev = [(torch.from_numpy(np.ascontiguousarray(s)).cuda(), torch.from_numpy(np.ascontiguousarray(t)).cuda())
+           for s, t, _ in pairs]
+    pin = [(torch.from_numpy(np.ascontiguousarray(s)).pin_memory(), torch.from_numpy(np.ascontiguousarray(t)).pin_memory())
+           for s, t, _ in pairs]
+    dev_list = [(dev[i][0].data_ptr(), dev[i][0].shape[0], dev[i][1].data_ptr(), dev[i][1].shape[0]) for i in order]
+    pin_list = [(pin[i][0].numpy(), pin[i][1].numpy()) for i in order]
+    ctxs = [capi.Context(local_rank) for _ in range(args.contexts)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    step_dev = lambda: capi.run_batch(ctxs, dev_list, params, device_inputs=True)  # noqa: E731
+    step_host = lambda: capi.run_batch(ctxs, pin_list, params, device_inputs=False)  # noqa: E731
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, out = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    T_dev, stats = out
+    launches = int(sum(s.kernel_launches for s in stats)) * args.steps
+    value = world * P * args.steps / (ms / 1e3)
+
+    step_host()  # warm the host path
+    ms_h, out_h = timed(step_host, args.steps)
+    e2e_value = world * P * args.steps / (ms_h / 1e3)
+    h2d = int(sum((len(pin_list[i][0]) + len(pin_list[i][1])) * 24 for i in range(P)))
+    d2h = int(P * (16 * 8 + 4))  # 4x4 result + done flag polls are counted per pair once; state copy adds <1 KB
+
+    # accuracy of what was timed (not part of the timed region)
+    errs = [(W.rotation_error(T_dev[j], pairs[order[j]][2]), float(np.linalg.norm(T_dev[j][:3, 3] - pairs[order[j]][2][:3, 3])))
+            for j in range(P)]
+
+    result = None
+    if rank == 0:
+        # roofline of the dominant kernel, measured live on the stream it runs on
+        c0 = ctxs[0]
+        s0, t0, _ = pairs[0]
+        c0.set_cloud_device(capi.SOURCE, dev[0][0].data_ptr(), len(s0))
+        c0.set_cloud_device(capi.TARGET, dev[0][1].data_ptr(), len(t0))
+        _, st0 = c0.run(params)
+        ms_nn = c0.time_stage(capi.STAGE_NN_SE3, 10)
+        stage_ms = {"nn_se3_sweep": ms_nn, "nn_xyz": c0.time_stage(capi.STAGE_NN_XYZ, 10),
+                    "reduce_gicp": c0.time_stage(capi.STAGE_REDUCE, 10), "knn_features_target": c0.time_stage(capi.STAGE_KNN_TARGET, 3)}
+        n, m = len(s0), len(t0)
+        alg_bytes = 48 * n + 48 * m + 8 * n
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / (ms_nn * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "nn_se3_brute_kernel", "algorithmic_bytes": alg_bytes,
+                    "kernel_ms": ms_nn, "peak_source": peak_src,
+                    "queries_per_s": n / (ms_nn * 1e-3), "pairs_per_s": n * m / (ms_nn * 1e-3),
+                    "iterations": st0.num_iterations, "se3_iterations": st0.num_pure_se3_iterations,
+                    "single_pair_ms": st0.time_total_ms, "single_pair_setup_ms": st0.time_setup_ms,
+                    "stage_ms": stage_ms}
+        # CPU baseline: the oracle port on one full-size pair of the same workload
+        orc = graft.load_oracle()
+        dt, T_cpu, st_cpu = cpu_reference_step(orc, pairs[0])
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": "1 pair (%d/%d points), %.1f s, %d iterations" % (n, m, dt, st_cpu.num_iterations),
+               "parity_vs_gpu": {"rot_rad": W.rotation_error(T_cpu, T_dev[0]),
+                                 "transl": float(np.linalg.norm(T_cpu[:3, 3] - T_dev[0][:3, 3])),
+                                 "iterations_cpu": st_cpu.num_iterations, "iterations_gpu": stats[0].num_iterations}}
+        result = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (f32 candidate sweep, exact f64 decisions)", "data": "synthetic",
+            "config": config_dict(args, pairs, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_h / args.steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "accuracy": {"max_rot_err_rad_vs_gt": max(e[0] for e in errs), "max_transl_err_m_vs_gt": max(e[1] for e in errs)},
+            "contexts_per_gpu": args.contexts,
+        }
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,317 @@
+"""ctypes binding of the C ABI declared in include/se3icp.h (libse3icp_cuda.so).
+
+The shared library is the product; this module only marshals numpy arrays across the boundary.
+There is no CPU fallback: if the library is missing or no sm_100 device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libse3icp_cuda.so")
+
+PT2PT, PT2PL, GICP = 0, 1, 2
+RUN_ICP, RUN_SE3_ICP, RUN_SE3_ICP_CF, RUN_SE3_PURE = 0, 1, 2, 3
+NN_AUTO, NN_BRUTE_F32, NN_EXACT_F64, NN_TREE, NN_TENSOR = 0, 1, 2, 3, 4
+SOURCE, TARGET = 0, 1
+STAGE_NN_SE3, STAGE_NN_XYZ, STAGE_REDUCE, STAGE_KNN_TARGET = 0, 1, 2, 3
+VARIANTS = {"pt2pt": PT2PT, "pt2pl": PT2PL, "gicp": GICP}
+MAX_KNN = 128
+
+STATUS = {0: "OK", 1: "ERR_ARG", 2: "ERR_NO_DEVICE", 3: "ERR_CUDA", 4: "ERR_NCCL", 5: "ERR_UNSUPPORTED", 6: "ERR_STATE"}
+
+
+class Se3IcpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("se3icp status %d (%s): %s" % (code, STATUS.get(code, "?"), msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int32),
+        ("entry", C.c_int32),
+        ("max_num_iterations", C.c_int32),
+        ("max_num_se3_iterations", C.c_int32),
+        ("number_of_nn_for_LRF", C.c_int32),
+        ("knn_normals_pt2pl", C.c_int32),
+        ("knn_normals_gicp", C.c_int32),
+        ("trim_keep_largest", C.c_int32),
+        ("mse", C.c_double),
+        ("mse_switch_error", C.c_double),
+        ("estimated_overlap", C.c_double),
+        ("alpha_rot", C.c_double),
+        ("beta_transl", C.c_double),
+        ("scale_preprocessing", C.c_double),
+        ("gicp_epsilon", C.c_double),
+        ("nn_mode", C.c_int32),
+        ("use_graph", C.c_int32),
+        ("record_history", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("num_iterations", C.c_int32),
+        ("num_pure_se3_iterations", C.c_int32),
+        ("scaling_factor", C.c_double),
+        ("time_total_ms", C.c_double),
+        ("time_setup_ms", C.c_double),
+        ("time_se3_correspondence_search_ms", C.c_double),
+        ("time_before_pure_icp_ms", C.c_double),
+        ("exact_repairs", C.c_int64),
+        ("kernel_launches", C.c_int64),
+    ]
+
+
+EXPORTED_SYMBOLS = [
+    "se3icp_abi_version", "se3icp_last_error", "se3icp_default_params", "se3icp_create", "se3icp_destroy",
+    "se3icp_synchronize", "se3icp_set_cloud", "se3icp_set_cloud_device", "se3icp_run", "se3icp_run_async",
+    "se3icp_run_finish", "se3icp_get_history", "se3icp_get_correspondences", "se3icp_get_se3_cloud",
+    "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_run_sharded", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
+    "se3icp_normals", "se3icp_gicp_cov", "se3icp_nn_se3", "se3icp_nn_xyz", "se3icp_trim", "se3icp_reduce_pt2pt",
+    "se3icp_reduce_pt2pl", "se3icp_reduce_gicp", "se3icp_solve",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libse3icp_cuda.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                "%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C se3-icp_b200/csrc)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.se3icp_last_error.restype = C.c_char_p
+        _lib.se3icp_abi_version.restype = C.c_int
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Se3IcpError(rc, lib().se3icp_last_error().decode("utf-8", "replace"))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def default_params(**kw):
+    p = Params()
+    lib().se3icp_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "variant" and isinstance(v, str):
+            v = VARIANTS[v]
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    """One registration context = one CUDA stream + the device memory of one source/target pair."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        _check(lib().se3icp_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.n = [0, 0]
+
+    def close(self):
+        if self._h:
+            lib().se3icp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        _check(lib().se3icp_synchronize(self._h))
+
+    def set_cloud(self, which, xyz, append=False):
+        xyz = _f64(xyz)
+        assert xyz.ndim == 2 and xyz.shape[1] == 3
+        _check(lib().se3icp_set_cloud(self._h, int(which), _dp(xyz), C.c_size_t(xyz.shape[0]), int(append)))
+        self.n[which] = xyz.shape[0] + (self.n[which] if append else 0)
+
+    def set_cloud_device(self, which, dev_ptr, n):
+        _check(lib().se3icp_set_cloud_device(self._h, int(which), C.c_void_p(int(dev_ptr)), C.c_size_t(n)))
+        self.n[which] = n
+
+    def run(self, params):
+        T = np.zeros((4, 4))
+        st = Stats()
+        _check(lib().se3icp_run(self._h, C.byref(params), _dp(T), C.byref(st)))
+        return T, st
+
+    def run_async(self, params):
+        _check(lib().se3icp_run_async(self._h, C.byref(params)))
+
+    def run_finish(self):
+        T = np.zeros((4, 4))
+        st = Stats()
+        _check(lib().se3icp_run_finish(self._h, _dp(T), C.byref(st)))
+        return T, st
+
+    def history(self, max_entries=1024):
+        buf = np.zeros((max_entries, 4, 4))
+        n = C.c_int(0)
+        _check(lib().se3icp_get_history(self._h, _dp(buf), int(max_entries), C.byref(n)))
+        return buf[:min(n.value, max_entries)]
+
+    def correspondences(self):
+        n = self.n[SOURCE]
+        idx = np.zeros(n, np.int32)
+        dist = np.zeros(n)
+        _check(lib().se3icp_get_correspondences(self._h, _ip(idx), _dp(dist), C.c_size_t(n)))
+        return idx, dist
+
+    def se3_cloud(self, which):
+        n = self.n[which]
+        fr = np.zeros((n, 4, 4))
+        _check(lib().se3icp_get_se3_cloud(self._h, int(which), _dp(fr), C.c_size_t(n)))
+        return fr
+
+    def time_stage(self, stage, repeats=10):
+        """average launch duration (ms) of one hot-path kernel on the data of the last run (CUDA events)"""
+        ms = C.c_double(0)
+        _check(lib().se3icp_time_stage(self._h, int(stage), int(repeats), C.byref(ms)))
+        return ms.value
+
+    # ---- stage-level entry points -------------------------------------------------------------
+    def knn(self, xyz, k):
+        xyz = _f64(xyz)
+        n = xyz.shape[0]
+        idx = np.zeros((n, k), np.int32)
+        d2 = np.zeros((n, k))
+        _check(lib().se3icp_knn(self._h, _dp(xyz), C.c_size_t(n), int(k), _ip(idx), _dp(d2)))
+        return idx, d2
+
+    def lrf(self, xyz, k):
+        xyz = _f64(xyz)
+        n = xyz.shape[0]
+        fr = np.zeros((n, 4, 4))
+        _check(lib().se3icp_lrf(self._h, _dp(xyz), C.c_size_t(n), int(k), _dp(fr)))
+        return fr
+
+    def normals(self, xyz, k):
+        xyz = _f64(xyz)
+        n = xyz.shape[0]
+        out = np.zeros((n, 3))
+        _check(lib().se3icp_normals(self._h, _dp(xyz), C.c_size_t(n), int(k), _dp(out)))
+        return out
+
+    def gicp_cov(self, normals, eps=1e-3):
+        normals = _f64(normals)
+        n = normals.shape[0]
+        out = np.zeros((n, 3, 3))
+        _check(lib().se3icp_gicp_cov(self._h, _dp(normals), C.c_size_t(n), C.c_double(eps), _dp(out)))
+        return out
+
+    def nn_se3(self, src_rows, tgt_rows, nn_mode=NN_AUTO):
+        src_rows, tgt_rows = _f64(src_rows), _f64(tgt_rows)
+        n, m = src_rows.shape[0], tgt_rows.shape[0]
+        idx = np.zeros(n, np.int32)
+        d2 = np.zeros(n)
+        rep = C.c_int64(0)
+        _check(lib().se3icp_nn_se3(self._h, _dp(src_rows), C.c_size_t(n), _dp(tgt_rows), C.c_size_t(m), int(nn_mode),
+                                   _ip(idx), _dp(d2), C.byref(rep)))
+        return idx, d2, rep.value
+
+    def nn_xyz(self, queries, tgt):
+        queries, tgt = _f64(queries), _f64(tgt)
+        n, m = queries.shape[0], tgt.shape[0]
+        idx = np.zeros(n, np.int32)
+        d2 = np.zeros(n)
+        _check(lib().se3icp_nn_xyz(self._h, _dp(queries), C.c_size_t(n), _dp(tgt), C.c_size_t(m), _ip(idx), _dp(d2)))
+        return idx, d2
+
+    def trim(self, dist, overlap, keep_largest=False):
+        dist = np.ascontiguousarray(dist, dtype=np.float32)
+        n = dist.shape[0]
+        keep = np.zeros(n, np.uint8)
+        nk = C.c_int64(0)
+        _check(lib().se3icp_trim(self._h, dist.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(n), C.c_double(overlap),
+                                 int(keep_largest), keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nk)))
+        return nk.value, keep.astype(bool)
+
+    def reduce_pt2pt(self, src, tgt, corr_tgt):
+        src, tgt = _f64(src), _f64(tgt)
+        corr = np.ascontiguousarray(corr_tgt, np.int32)
+        T = np.zeros((4, 4))
+        _check(lib().se3icp_reduce_pt2pt(self._h, _dp(src), C.c_size_t(src.shape[0]), _dp(tgt), C.c_size_t(tgt.shape[0]),
+                                         _ip(corr), _dp(T)))
+        return T
+
+    def reduce_pt2pl(self, src, tgt, tgt_normals, corr_tgt):
+        src, tgt, tgt_normals = _f64(src), _f64(tgt), _f64(tgt_normals)
+        corr = np.ascontiguousarray(corr_tgt, np.int32)
+        out = np.zeros(27)
+        _check(lib().se3icp_reduce_pt2pl(self._h, _dp(src), C.c_size_t(src.shape[0]), _dp(tgt), _dp(tgt_normals),
+                                         C.c_size_t(tgt.shape[0]), _ip(corr), _dp(out)))
+        return out
+
+    def reduce_gicp(self, src, src_cov, tgt, tgt_cov, corr_tgt, conf_src=None, conf_tgt=None):
+        src, tgt, src_cov, tgt_cov = _f64(src), _f64(tgt), _f64(src_cov), _f64(tgt_cov)
+        corr = np.ascontiguousarray(corr_tgt, np.int32)
+        cs = _dp(_f64(conf_src)) if conf_src is not None else None
+        ct = _dp(_f64(conf_tgt)) if conf_tgt is not None else None
+        out = np.zeros(27)
+        _check(lib().se3icp_reduce_gicp(self._h, _dp(src), _dp(src_cov), C.c_size_t(src.shape[0]), _dp(tgt), _dp(tgt_cov),
+                                        C.c_size_t(tgt.shape[0]), _ip(corr), cs, ct, _dp(out)))
+        return out
+
+    def solve(self, in27):
+        in27 = _f64(in27)
+        T = np.zeros((4, 4))
+        _check(lib().se3icp_solve(self._h, _dp(in27), _dp(T)))
+        return T
+
+
+def run_batch(ctxs, pairs, params, device_inputs=False):
+    """pairs: list of (src, tgt) numpy arrays (host) or (src_ptr, n_src, tgt_ptr, n_tgt) device tuples."""
+    n_pairs = len(pairs)
+    n_ctx = len(ctxs)
+    handles = (C.c_void_p * n_ctx)(*[c.handle for c in ctxs])
+    srcp = (C.c_void_p * n_pairs)()
+    tgtp = (C.c_void_p * n_pairs)()
+    ns = (C.c_size_t * n_pairs)()
+    nt = (C.c_size_t * n_pairs)()
+    keep = []
+    for i, pr in enumerate(pairs):
+        if device_inputs:
+            srcp[i], ns[i], tgtp[i], nt[i] = int(pr[0]), int(pr[1]), int(pr[2]), int(pr[3])
+        else:
+            s, t = _f64(pr[0]), _f64(pr[1])
+            keep.append((s, t))
+            srcp[i], ns[i], tgtp[i], nt[i] = s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0]
+    T = np.zeros((n_pairs, 4, 4))
+    stats = (Stats * n_pairs)()
+    fn = lib().se3icp_run_batch_device if device_inputs else lib().se3icp_run_batch
+    _check(fn(handles, n_ctx, n_pairs, srcp, ns, tgtp, nt, C.byref(params), _dp(T), stats))
+    return T, list(stats)

@@ -1,0 +1,1028 @@
+// capi.cu — C ABI (include/se3icp.h): context management, the registration driver that enqueues the
+// kernels of spatial_index.cu / knn_features.cu / nn_search.cu / optimise.cu, the batch runner and
+// the stage-level entry points used by the parity tests.  No CPU fallback anywhere: every entry
+// point fails with a status code when CUDA fails.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "context.h"
+#include "internal.h"
+
+namespace se3 {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DeviceBuf::ensure(size_t bytes) {
+    if (bytes <= cap && ptr) return 0;
+    release();
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        cap = 0;
+        set_last_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+        return SE3ICP_ERR_CUDA;
+    }
+    cap = want;
+    return 0;
+}
+
+int DeviceBuf::ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
+    if (bytes <= cap && ptr) return 0;
+    void* np = nullptr;
+    size_t want = bytes + bytes / 2;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) {
+        set_last_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+        return SE3ICP_ERR_CUDA;
+    }
+    if (ptr && keep) {
+        cudaMemcpyAsync(np, ptr, keep, cudaMemcpyDeviceToDevice, st);
+        cudaStreamSynchronize(st);
+    }
+    release();
+    ptr = np;
+    cap = want;
+    return 0;
+}
+
+void DeviceBuf::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+}  // namespace se3
+
+using namespace se3;
+
+SourceView se3icp_ctx::source_view() const {
+    SourceView S;
+    S.n = (int)n[0];
+    S.x = index[0].x.as<double>();
+    S.y = index[0].y.as<double>();
+    S.z = index[0].z.as<double>();
+    S.frame = frame[0].as<double>();
+    S.cov = cov[0].as<double>();
+    S.conf = conf[0].as<double>();
+    return S;
+}
+
+TargetView se3icp_ctx::target_view() const {
+    TargetView T;
+    T.n = (int)n[1];
+    T.idx = index[1].view;
+    T.nrm = nrm[1].as<double>();
+    T.cov = cov[1].as<double>();
+    T.conf = conf[1].as<double>();
+    T.rows32 = rows32.as<float4>();
+    T.rows64 = rows64.as<double>();
+    T.box12 = nullptr;
+    return T;
+}
+
+CorrBuffers se3icp_ctx::corr_buffers(bool with_d2) const {
+    CorrBuffers cb;
+    cb.d2_nd = with_d2 ? d2_nd.as<double>() : nullptr;
+    cb.idx = corr_idx.as<int>();
+    cb.dist = corr_dist.as<double>();
+    cb.distf = corr_distf.as<float>();
+    cb.keep = keep.as<uint8_t>();
+    cb.repair = repair.as<int>();
+    return cb;
+}
+
+namespace {
+
+// PCL CorrespondenceRejectorTrimmed: overlap stored as float; floor(ratio * float(N)) as unsigned
+size_t trimmed_count(size_t n, double overlap) {
+    float ratio = (float)overlap;
+    float prod = ratio * static_cast<float>(n);
+    double fl = std::floor((double)prod);
+    if (fl < 0.0) fl = 0.0;
+    if (fl > 4294967295.0) fl = 4294967295.0;
+    return (size_t)(unsigned int)fl;
+}
+
+int fill_config(se3icp_ctx* c, const se3icp_params* p) {
+    if (p->entry < SE3ICP_RUN_ICP || p->entry > SE3ICP_RUN_SE3_PURE) {
+        set_last_error("bad entry %d", p->entry);
+        return SE3ICP_ERR_ARG;
+    }
+    if (p->variant < SE3ICP_PT2PT || p->variant > SE3ICP_GICP) {
+        set_last_error("bad variant %d (valid: pt2pt, pt2pl, gicp)", p->variant);
+        return SE3ICP_ERR_ARG;
+    }
+    RunConfig& cfg = c->cfg;
+    cfg.entry = p->entry;
+    cfg.with_cf = p->entry == SE3ICP_RUN_SE3_ICP_CF;
+    cfg.variant = cfg.with_cf ? (int)SE3ICP_GICP : p->variant;  // .cpp:855-856,921: GICP hard-wired
+    cfg.max_iter = p->max_num_iterations;
+    cfg.max_se3_iter = p->max_num_se3_iterations;
+    cfg.has_se3 = p->entry != SE3ICP_RUN_ICP;
+    cfg.pure = p->entry == SE3ICP_RUN_SE3_PURE;
+    size_t N = c->n[0];
+    size_t keep = trimmed_count(N, p->estimated_overlap);
+    cfg.trim_active = keep < N;
+    cfg.n_keep_target = (int)std::min(keep, N);
+    cfg.keep_largest = p->trim_keep_largest != 0;
+    cfg.record_history = p->record_history != 0;
+    long cap = std::max<long>(std::max(p->max_num_iterations, p->max_num_se3_iterations), 1);
+    cfg.max_history = (int)std::min<long>(cap, 100000);
+    cfg.mse = p->mse;
+    cfg.mse_switch = p->mse_switch_error;
+    cfg.alpha = p->alpha_rot;
+    cfg.beta = p->beta_transl;
+    c->params = *p;
+    return 0;
+}
+
+int alloc_run(se3icp_ctx* c) {
+    const RunConfig& cfg = c->cfg;
+    size_t N = c->n[0], M = c->n[1];
+    SE3_TRY(c->index[0].reserve((int)N));
+    SE3_TRY(c->index[1].reserve((int)M));
+    for (int w = 0; w < 2; w++) {
+        size_t nn = c->n[w];
+        if (cfg.has_se3) SE3_TRY(c->frame[w].ensure(9 * nn * sizeof(double)));
+        if (cfg.variant == SE3ICP_GICP || (w == 1 && cfg.variant == SE3ICP_PT2PL))
+            SE3_TRY(c->nrm[w].ensure(3 * nn * sizeof(double)));
+        if (cfg.variant == SE3ICP_GICP) SE3_TRY(c->cov[w].ensure(6 * nn * sizeof(double)));
+        if (cfg.with_cf) SE3_TRY(c->conf[w].ensure(nn * sizeof(double)));
+        SE3_TRY(c->psum[w].ensure((size_t)kReduceBlocks * 3 * sizeof(double)));
+        SE3_TRY(c->pmax[w].ensure((size_t)kReduceBlocks * sizeof(double)));
+    }
+    if (cfg.has_se3) {
+        SE3_TRY(c->rows32.ensure(3 * M * sizeof(float4)));
+        SE3_TRY(c->rows64.ensure(12 * M * sizeof(double)));
+    }
+    SE3_TRY(c->corr_idx.ensure(N * sizeof(int)));
+    SE3_TRY(c->corr_dist.ensure(N * sizeof(double)));
+    SE3_TRY(c->corr_distf.ensure(N * sizeof(float)));
+    SE3_TRY(c->keep.ensure(N));
+    SE3_TRY(c->repair.ensure(N * sizeof(int)));
+    SE3_TRY(c->d2_nd.ensure(N * sizeof(double)));
+    SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));
+    SE3_TRY(c->hist.ensure(4 * 256 * sizeof(unsigned int)));
+    SE3_TRY(c->block_eq.ensure((size_t)kReduceBlocks * sizeof(int)));
+    if (cfg.record_history) SE3_TRY(c->history.ensure((size_t)cfg.max_history * 16 * sizeof(double)));
+    SE3_TRY(c->state.ensure(sizeof(IterState)));
+    return 0;
+}
+
+int enqueue_setup(se3icp_ctx* c) {
+    const RunConfig& cfg = c->cfg;
+    const se3icp_params& p = c->params;
+    cudaStream_t st = c->stream;
+    int N = (int)c->n[0], M = (int)c->n[1];
+    const double* rs = c->raw_view[0];
+    const double* rt = c->raw_view[1];
+    IterState* ds = c->dstate();
+
+    SE3_TRY(launch_init_state(ds, c->hist.as<unsigned int>(), st));
+    c->launches += 1;
+    if (cfg.has_se3) {
+        if (cfg.with_cf) {  // .cpp:756-769: confidences from the raw depth, before normalisation
+            SE3_TRY(launch_confidence(rs, N, c->conf[0].as<double>(), st));
+            SE3_TRY(launch_confidence(rt, M, c->conf[1].as<double>(), st));
+            c->launches += 2;
+        }
+        SE3_TRY(launch_sum_xyz(rs, N, c->psum[0].as<double>(), st));
+        SE3_TRY(launch_sum_xyz(rt, M, c->psum[1].as<double>(), st));
+        SE3_TRY(launch_maxdist(rs, N, c->psum[0].as<double>(), c->pmax[0].as<double>(), st));
+        SE3_TRY(launch_maxdist(rt, M, c->psum[1].as<double>(), c->pmax[1].as<double>(), st));
+        SE3_TRY(launch_normalise(rs, N, c->psum[0].as<double>(), c->pmax[0].as<double>(), c->pmax[1].as<double>(), N, M,
+                                 p.scale_preprocessing, SE3ICP_SOURCE, ds, c->index[0].x.as<double>(),
+                                 c->index[0].y.as<double>(), c->index[0].z.as<double>(), st));
+        SE3_TRY(launch_normalise(rt, M, c->psum[1].as<double>(), c->pmax[0].as<double>(), c->pmax[1].as<double>(), N, M,
+                                 p.scale_preprocessing, SE3ICP_TARGET, ds, c->index[1].x.as<double>(),
+                                 c->index[1].y.as<double>(), c->index[1].z.as<double>(), st));
+        c->launches += 6;
+    } else {
+        SE3_TRY(launch_aos_to_soa(rs, N, c->index[0].x.as<double>(), c->index[0].y.as<double>(),
+                                  c->index[0].z.as<double>(), st));
+        SE3_TRY(launch_aos_to_soa(rt, M, c->index[1].x.as<double>(), c->index[1].y.as<double>(),
+                                  c->index[1].z.as<double>(), st));
+        c->launches += 2;
+    }
+    SE3_TRY(c->index[1].build(st, &c->launches));
+    const bool need_src_index = cfg.has_se3 || cfg.variant == SE3ICP_GICP;
+    if (need_src_index) SE3_TRY(c->index[0].build(st, &c->launches));
+
+    for (int w = 0; w < 2; w++) {
+        FeatureArgs fa{};
+        fa.k_lrf = cfg.has_se3 ? p.number_of_nn_for_LRF : 0;
+        if (cfg.variant == SE3ICP_GICP)
+            fa.k_nrm = p.knn_normals_gicp;  // .cpp:43 both clouds
+        else if (cfg.variant == SE3ICP_PT2PL && w == 1)
+            fa.k_nrm = p.knn_normals_pt2pl;  // .cpp:494,643 target only
+        fa.want_cov = cfg.variant == SE3ICP_GICP;
+        fa.gicp_eps = p.gicp_epsilon;
+        fa.frame = c->frame[w].as<double>();
+        fa.nrm = c->nrm[w].as<double>();
+        fa.cov = c->cov[w].as<double>();
+        fa.K = std::max(fa.k_lrf, fa.k_nrm);
+        if (fa.K <= 0) continue;
+        SE3_TRY(launch_knn_features(c->index[w].view, fa, st));
+        c->launches += 1;
+    }
+    if (cfg.has_se3) {
+        SE3_TRY(launch_pack_target_rows(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.beta, cfg.with_cf,
+                                        c->rows32.as<float4>(), c->rows64.as<double>(), ds, st));
+        c->launches += 1;
+    }
+    SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, (size_t)N * sizeof(int), st));
+    if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
+    return 0;
+}
+
+int enqueue_iteration(se3icp_ctx* c) {
+    const RunConfig& cfg = c->cfg;
+    cudaStream_t st = c->stream;
+    SourceView S = c->source_view();
+    TargetView T = c->target_view();
+    CorrBuffers cb = c->corr_buffers(false);
+    IterState* ds = c->dstate();
+    if (cfg.has_se3) {
+        int force = c->params.nn_mode == SE3ICP_NN_EXACT_F64;
+        SE3_TRY(launch_nn_se3_brute(S, T, cfg, ds, cb, force, st));
+        SE3_TRY(launch_nn_se3_repair(S, T, cfg, ds, cb, st));
+        c->launches += 2;
+    }
+    if (!cfg.pure) {
+        SE3_TRY(launch_nn_xyz(S, T, cfg, ds, cb, st));
+        c->launches += 1;
+    }
+    if (cfg.trim_active && cfg.n_keep_target > 0) {
+        SE3_TRY(launch_trim(cfg, ds, cb, S.n, c->hist.as<unsigned int>(), c->block_eq.as<int>(), st));
+        c->launches += 6;
+    }
+    SE3_TRY(launch_reduce(S, T, cfg, ds, cb, c->partials.as<double>(), st));
+    SE3_TRY(launch_solve_update(cfg, ds, c->partials.as<double>(), c->history.as<double>(), c->hist.as<unsigned int>(), st));
+    c->launches += 2;
+    return 0;
+}
+
+int check_ctx(se3icp_ctx* c) {
+    if (!c) {
+        set_last_error("null context");
+        return SE3ICP_ERR_ARG;
+    }
+    SE3_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int se3icp_abi_version(void) { return SE3ICP_ABI_VERSION; }
+const char* se3icp_last_error(void) { return se3::g_err; }
+
+void se3icp_default_params(se3icp_params* p) {  // reference ctor .cpp:334-348
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->variant = SE3ICP_PT2PL;
+    p->entry = SE3ICP_RUN_SE3_ICP;
+    p->max_num_iterations = 150;
+    p->max_num_se3_iterations = 20;
+    p->number_of_nn_for_LRF = 30;
+    p->knn_normals_pt2pl = 30;
+    p->knn_normals_gicp = 20;
+    p->trim_keep_largest = 0;
+    p->mse = 0.00001;
+    p->mse_switch_error = 0.001;
+    p->estimated_overlap = 1.0;
+    p->alpha_rot = 3.0;
+    p->beta_transl = 1.0;
+    p->scale_preprocessing = 3.0;
+    p->gicp_epsilon = 1e-3;
+    p->nn_mode = SE3ICP_NN_AUTO;
+    p->use_graph = 0;
+    p->record_history = 0;
+}
+
+int se3icp_create(int device, void* stream, se3icp_ctx** out) {
+    if (!out) return SE3ICP_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        set_last_error("no usable CUDA device %d (count %d, %s)", device, count, cudaGetErrorString(e));
+        return SE3ICP_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    SE3_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_last_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return SE3ICP_ERR_NO_DEVICE;
+    }
+    SE3_CUDA(cudaSetDevice(device));
+    se3icp_ctx* c = new se3icp_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            set_last_error("cudaStreamCreate failed");
+            return SE3ICP_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    if (cudaMallocHost((void**)&c->h_state, sizeof(IterState)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_flag, 64) != cudaSuccess || cudaEventCreate(&c->ev_begin) != cudaSuccess ||
+        cudaEventCreate(&c->ev_setup) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess) {
+        set_last_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        se3icp_destroy(c);
+        return SE3ICP_ERR_CUDA;
+    }
+    *out = c;
+    return SE3ICP_OK;
+}
+
+int se3icp_destroy(se3icp_ctx* c) {
+    if (!c) return SE3ICP_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_setup) cudaEventDestroy(c->ev_setup);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SE3ICP_OK;
+}
+
+int se3icp_synchronize(se3icp_ctx* c) {
+    SE3_TRY(check_ctx(c));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return SE3ICP_OK;
+}
+
+int se3icp_set_cloud(se3icp_ctx* c, int which, const double* xyz, size_t n, int append) {
+    SE3_TRY(check_ctx(c));
+    if ((which != SE3ICP_SOURCE && which != SE3ICP_TARGET) || (!xyz && n > 0)) {
+        set_last_error("se3icp_set_cloud: bad argument");
+        return SE3ICP_ERR_ARG;
+    }
+    if (n > 0x7fffffffULL / 4) return SE3ICP_ERR_UNSUPPORTED;
+    size_t old = append ? c->n[which] : 0;
+    if (append && c->raw_view[which] != c->raw[which].ptr && old > 0) {
+        set_last_error("cannot append to a caller-owned device cloud");
+        return SE3ICP_ERR_STATE;
+    }
+    size_t total = old + n;
+    SE3_TRY(c->raw[which].ensure_keep(total * 3 * sizeof(double), old * 3 * sizeof(double), c->stream));
+    if (n > 0)
+        SE3_CUDA(cudaMemcpyAsync(c->raw[which].as<double>() + old * 3, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                                 c->stream));
+    c->raw_view[which] = c->raw[which].as<double>();
+    c->n[which] = total;
+    return SE3ICP_OK;
+}
+
+int se3icp_set_cloud_device(se3icp_ctx* c, int which, const double* d_xyz, size_t n) {
+    SE3_TRY(check_ctx(c));
+    if ((which != SE3ICP_SOURCE && which != SE3ICP_TARGET) || !d_xyz || n == 0) return SE3ICP_ERR_ARG;
+    c->raw_view[which] = d_xyz;
+    c->n[which] = n;
+    return SE3ICP_OK;
+}
+
+int se3icp_run_async(se3icp_ctx* c, const se3icp_params* p) {
+    SE3_TRY(check_ctx(c));
+    if (!p) return SE3ICP_ERR_ARG;
+    if (c->n[0] == 0 || c->n[1] == 0 || !c->raw_view[0] || !c->raw_view[1]) {
+        set_last_error("source/target cloud not set");
+        return SE3ICP_ERR_STATE;
+    }
+    if (p->number_of_nn_for_LRF > SE3ICP_MAX_KNN || p->knn_normals_gicp > SE3ICP_MAX_KNN ||
+        p->knn_normals_pt2pl > SE3ICP_MAX_KNN) {
+        set_last_error("kNN sizes above %d are not supported", SE3ICP_MAX_KNN);
+        return SE3ICP_ERR_UNSUPPORTED;
+    }
+    SE3_TRY(fill_config(c, p));
+    SE3_TRY(alloc_run(c));
+    c->launches = 0;
+    SE3_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+    SE3_TRY(enqueue_setup(c));
+    SE3_CUDA(cudaEventRecord(c->ev_setup, c->stream));
+    // Iterations: the stop/phase decision lives on the device (solve_update); the host only polls the
+    // done flag.  Every kernel early-outs once done is set, so over-issuing is harmless.
+    const long hard_cap = 1000000;
+    for (long it = 0; it < hard_cap; ++it) {
+        SE3_TRY(enqueue_iteration(c));
+        SE3_CUDA(cudaMemcpyAsync(c->h_flag, &c->dstate()->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+        if (*c->h_flag) break;
+    }
+    SE3_TRY(launch_finalize(c->cfg, c->dstate(), c->stream));
+    c->launches += 1;
+    SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaEventRecord(c->ev_end, c->stream));
+    c->run_pending = true;
+    return SE3ICP_OK;
+}
+
+int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
+    SE3_TRY(check_ctx(c));
+    if (!c->run_pending) {
+        set_last_error("no run pending");
+        return SE3ICP_ERR_STATE;
+    }
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    c->run_pending = false;
+    const IterState& hs = *c->h_state;
+    if (T_out) memcpy(T_out, hs.T_final, 16 * sizeof(double));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->num_iterations = hs.iter;
+        stats->num_pure_se3_iterations = c->cfg.has_se3 ? hs.se3_iters : -1;
+        stats->scaling_factor = hs.scale;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end);
+        stats->time_total_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev_begin, c->ev_setup);
+        stats->time_setup_ms = ms;
+        stats->time_se3_correspondence_search_ms = (double)hs.t_corr_ns / 1e6;
+        stats->time_before_pure_icp_ms = stats->time_total_ms;  // .cpp:957-958 measures the whole call
+        stats->exact_repairs = hs.total_repairs;
+        stats->kernel_launches = c->launches;
+    }
+    return SE3ICP_OK;
+}
+
+int se3icp_run(se3icp_ctx* c, const se3icp_params* p, double* T_out, se3icp_stats* stats) {
+    SE3_TRY(se3icp_run_async(c, p));
+    return se3icp_run_finish(c, T_out, stats);
+}
+
+int se3icp_get_history(se3icp_ctx* c, double* T_hist, int max_entries, int* n_out) {
+    SE3_TRY(check_ctx(c));
+    if (!n_out) return SE3ICP_ERR_ARG;
+    int cnt = c->h_state ? c->h_state->hist_count : 0;
+    if (!c->cfg.record_history) cnt = 0;
+    *n_out = cnt;
+    int k = std::min(cnt, max_entries);
+    if (k > 0 && T_hist) {
+        SE3_CUDA(cudaMemcpyAsync(T_hist, c->history.ptr, (size_t)k * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return SE3ICP_OK;
+}
+
+int se3icp_get_correspondences(se3icp_ctx* c, int32_t* tgt_idx, double* dist, size_t n) {
+    SE3_TRY(check_ctx(c));
+    if (n > c->n[0] || !c->corr_idx.ptr) return SE3ICP_ERR_ARG;
+    if (tgt_idx) SE3_CUDA(cudaMemcpyAsync(tgt_idx, c->corr_idx.ptr, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (dist) SE3_CUDA(cudaMemcpyAsync(dist, c->corr_dist.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return SE3ICP_OK;
+}
+
+// frames16: [alpha R | beta p] of the normalised cloud, as the reference leaves them after set-up
+// (source: additionally left-multiplied by the accumulated estimate, .cpp:713-716)
+int se3icp_get_se3_cloud(se3icp_ctx* c, int which, double* frames16, size_t n) {
+    SE3_TRY(check_ctx(c));
+    if ((which != 0 && which != 1) || !frames16 || n > c->n[which] || !c->cfg.has_se3 || !c->frame[which].ptr)
+        return SE3ICP_ERR_ARG;
+    size_t nn = c->n[which];
+    std::vector<double> fr(9 * nn), x(nn), y(nn), z(nn);
+    SE3_CUDA(cudaMemcpyAsync(fr.data(), c->frame[which].ptr, 9 * nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaMemcpyAsync(x.data(), c->index[which].x.ptr, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaMemcpyAsync(y.data(), c->index[which].y.ptr, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaMemcpyAsync(z.data(), c->index[which].z.ptr, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    const double a = c->cfg.alpha, b = c->cfg.beta;
+    const double* Tt = c->h_state->T_total;
+    for (size_t i = 0; i < n; i++) {
+        double X[16] = {0};
+        for (int col = 0; col < 3; col++)
+            for (int r = 0; r < 3; r++) X[4 * r + col] = a * fr[(size_t)(3 * col + r) * nn + i];
+        X[3] = b * x[i], X[7] = b * y[i], X[11] = b * z[i];
+        X[15] = 1.0;
+        double* o = frames16 + 16 * i;
+        if (which == SE3ICP_SOURCE) {
+            for (int r = 0; r < 4; r++)
+                for (int col = 0; col < 4; col++) {
+                    double s = 0;
+                    for (int k = 0; k < 4; k++) s += Tt[4 * r + k] * X[4 * k + col];
+                    o[4 * r + col] = s;
+                }
+        } else {
+            memcpy(o, X, sizeof(X));
+        }
+    }
+    return SE3ICP_OK;
+}
+
+// ---- batch of independent pairs: one host thread per context, contexts run concurrently on their streams
+static int run_batch_impl(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const double* const* src, const size_t* n_src,
+                          const double* const* tgt, const size_t* n_tgt, const se3icp_params* p, double* T_out,
+                          se3icp_stats* stats, bool device_inputs) {
+    if (!ctxs || n_ctx <= 0 || n_pairs < 0 || !src || !tgt || !n_src || !n_tgt || !p || !T_out) return SE3ICP_ERR_ARG;
+    std::vector<int> rc(n_ctx, 0);
+    std::vector<std::string> errs(n_ctx);
+    auto worker = [&](int ci) {
+        se3icp_ctx* c = ctxs[ci];
+        for (int pi = ci; pi < n_pairs; pi += n_ctx) {
+            int r;
+            if (device_inputs) {
+                r = se3icp_set_cloud_device(c, SE3ICP_SOURCE, src[pi], n_src[pi]);
+                if (!r) r = se3icp_set_cloud_device(c, SE3ICP_TARGET, tgt[pi], n_tgt[pi]);
+            } else {
+                r = se3icp_set_cloud(c, SE3ICP_SOURCE, src[pi], n_src[pi], 0);
+                if (!r) r = se3icp_set_cloud(c, SE3ICP_TARGET, tgt[pi], n_tgt[pi], 0);
+            }
+            if (!r) r = se3icp_run(c, p, T_out + 16 * (size_t)pi, stats ? stats + pi : nullptr);
+            if (r) {
+                rc[ci] = r;
+                errs[ci] = se3icp_last_error();
+                return;
+            }
+        }
+    };
+    if (n_ctx == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int ci = 0; ci < n_ctx; ci++) th.emplace_back(worker, ci);
+        for (auto& t : th) t.join();
+    }
+    for (int ci = 0; ci < n_ctx; ci++)
+        if (rc[ci]) {
+            set_last_error("%s", errs[ci].c_str());
+            return rc[ci];
+        }
+    return SE3ICP_OK;
+}
+
+int se3icp_run_batch(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const double* const* src, const size_t* n_src,
+                     const double* const* tgt, const size_t* n_tgt, const se3icp_params* p, double* T_out,
+                     se3icp_stats* stats) {
+    return run_batch_impl(ctxs, n_ctx, n_pairs, src, n_src, tgt, n_tgt, p, T_out, stats, false);
+}
+
+int se3icp_run_batch_device(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const double* const* d_src, const size_t* n_src,
+                            const double* const* d_tgt, const size_t* n_tgt, const se3icp_params* p, double* T_out,
+                            se3icp_stats* stats) {
+    return run_batch_impl(ctxs, n_ctx, n_pairs, d_src, n_src, d_tgt, n_tgt, p, T_out, stats, true);
+}
+
+int se3icp_run_sharded(se3icp_ctx* c, const se3icp_params* p, size_t src_begin, size_t src_end, void* nccl_comm,
+                       double* T_out, se3icp_stats* stats) {
+    (void)c, (void)p, (void)src_begin, (void)src_end, (void)nccl_comm, (void)T_out, (void)stats;
+    set_last_error("se3icp_run_sharded: not built yet");
+    return SE3ICP_ERR_UNSUPPORTED;
+}
+
+int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
+    SE3_TRY(check_ctx(c));
+    if (!ms_avg || repeats <= 0 || stage < SE3ICP_STAGE_NN_SE3 || stage > SE3ICP_STAGE_KNN_TARGET) return SE3ICP_ERR_ARG;
+    if (c->run_pending || c->n[0] == 0 || c->n[1] == 0 || !c->state.ptr) {
+        set_last_error("se3icp_time_stage needs a finished se3icp_run on this context");
+        return SE3ICP_ERR_STATE;
+    }
+    if ((stage == SE3ICP_STAGE_NN_SE3 && !c->cfg.has_se3) || (stage == SE3ICP_STAGE_NN_XYZ && c->cfg.pure))
+        return SE3ICP_ERR_STATE;
+    cudaStream_t st = c->stream;
+    IterState saved = *c->h_state;
+    IterState tmp = saved;
+    tmp.done = 0;
+    tmp.repair_count = 0;
+    tmp.switch_icp = stage == SE3ICP_STAGE_NN_SE3 ? 0 : 1;
+    SE3_CUDA(cudaMemcpyAsync(c->dstate(), &tmp, sizeof(IterState), cudaMemcpyHostToDevice, st));
+    SourceView S = c->source_view();
+    TargetView T = c->target_view();
+    CorrBuffers cb = c->corr_buffers(false);
+    RunConfig cfg = c->cfg;
+    cfg.pure = 0;
+    cudaEvent_t e0, e1;
+    SE3_CUDA(cudaEventCreate(&e0));
+    SE3_CUDA(cudaEventCreate(&e1));
+    double total = 0.0;
+    for (int r = -1; r < repeats; r++) {  // r == -1 is a warm-up launch
+        if (stage == SE3ICP_STAGE_NN_SE3)
+            SE3_CUDA(cudaMemsetAsync(&c->dstate()->repair_count, 0, sizeof(int), st));
+        SE3_CUDA(cudaEventRecord(e0, st));
+        switch (stage) {
+            case SE3ICP_STAGE_NN_SE3:
+                SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 0, st));
+                break;
+            case SE3ICP_STAGE_NN_XYZ:
+                SE3_TRY(launch_nn_xyz(S, T, cfg, c->dstate(), cb, st));
+                break;
+            case SE3ICP_STAGE_REDUCE:
+                SE3_TRY(launch_reduce(S, T, cfg, c->dstate(), cb, c->partials.as<double>(), st));
+                break;
+            default: {
+                FeatureArgs fa{};
+                fa.k_lrf = cfg.has_se3 ? c->params.number_of_nn_for_LRF : 0;
+                fa.k_nrm = cfg.variant == SE3ICP_GICP ? c->params.knn_normals_gicp
+                                                      : (cfg.variant == SE3ICP_PT2PL ? c->params.knn_normals_pt2pl : 0);
+                fa.want_cov = cfg.variant == SE3ICP_GICP;
+                fa.gicp_eps = c->params.gicp_epsilon;
+                fa.frame = c->frame[1].as<double>();
+                fa.nrm = c->nrm[1].as<double>();
+                fa.cov = c->cov[1].as<double>();
+                fa.K = std::max(fa.k_lrf, fa.k_nrm);
+                if (fa.K <= 0) return SE3ICP_ERR_STATE;
+                SE3_TRY(launch_knn_features(c->index[1].view, fa, st));
+            }
+        }
+        SE3_CUDA(cudaEventRecord(e1, st));
+        SE3_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SE3_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 0) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    SE3_CUDA(cudaMemcpyAsync(c->dstate(), &saved, sizeof(IterState), cudaMemcpyHostToDevice, st));
+    SE3_CUDA(cudaStreamSynchronize(st));
+    *ms_avg = total / repeats;
+    return SE3ICP_OK;
+}
+
+// ================================================================================================
+// stage-level entry points
+// ================================================================================================
+namespace {
+
+int upload_cloud_and_index(se3icp_ctx* c, int w, const double* xyz, size_t n) {
+    SE3_TRY(se3icp_set_cloud(c, w, xyz, n, 0));
+    SE3_TRY(c->index[w].reserve((int)n));
+    SE3_TRY(launch_aos_to_soa(c->raw_view[w], (int)n, c->index[w].x.as<double>(), c->index[w].y.as<double>(),
+                              c->index[w].z.as<double>(), c->stream));
+    SE3_TRY(c->index[w].build(c->stream, nullptr));
+    return 0;
+}
+
+// host row-major [n][d] -> device planes [d][n]
+int upload_planes(se3icp_ctx* c, DeviceBuf& dst, const double* rows, size_t n, int d, int stride, int col0) {
+    std::vector<double> planes((size_t)d * n);
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) planes[(size_t)k * n + i] = rows[i * stride + col0 + k];
+    SE3_TRY(dst.ensure(planes.size() * sizeof(double)));
+    SE3_CUDA(cudaMemcpyAsync(dst.ptr, planes.data(), planes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int download_planes(se3icp_ctx* c, const DeviceBuf& src, double* rows, size_t n, int d) {
+    std::vector<double> planes((size_t)d * n);
+    SE3_CUDA(cudaMemcpyAsync(planes.data(), src.ptr, planes.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) rows[i * d + k] = planes[(size_t)k * n + i];
+    return 0;
+}
+
+// 3x3 row-major covariances -> 6 symmetric planes
+int upload_cov(se3icp_ctx* c, DeviceBuf& dst, const double* cov9, size_t n) {
+    static const int map6[6] = {0, 1, 2, 4, 5, 8};
+    std::vector<double> planes(6 * n);
+    for (size_t i = 0; i < n; i++)
+        for (int e = 0; e < 6; e++) planes[(size_t)e * n + i] = cov9[9 * i + map6[e]];
+    SE3_TRY(dst.ensure(planes.size() * sizeof(double)));
+    SE3_CUDA(cudaMemcpyAsync(dst.ptr, planes.data(), planes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int stage_features(se3icp_ctx* c, const double* xyz, size_t n, int k_lrf, int k_nrm, int k_list, bool want_knn) {
+    if (!xyz || n == 0 || k_list <= 0) return SE3ICP_ERR_ARG;
+    if (k_list > SE3ICP_MAX_KNN) {
+        set_last_error("k = %d above SE3ICP_MAX_KNN", k_list);
+        return SE3ICP_ERR_UNSUPPORTED;
+    }
+    SE3_TRY(upload_cloud_and_index(c, 0, xyz, n));
+    FeatureArgs fa{};
+    fa.k_lrf = k_lrf;
+    fa.k_nrm = k_nrm;
+    fa.K = k_list;
+    if (k_lrf > 0) {
+        SE3_TRY(c->frame[0].ensure(9 * n * sizeof(double)));
+        fa.frame = c->frame[0].as<double>();
+    }
+    if (k_nrm > 0) {
+        SE3_TRY(c->nrm[0].ensure(3 * n * sizeof(double)));
+        fa.nrm = c->nrm[0].as<double>();
+    }
+    if (want_knn) {
+        SE3_TRY(c->scratch.ensure(n * (size_t)k_list * (sizeof(int) + sizeof(double))));
+        fa.knn_d2 = c->scratch.as<double>();
+        fa.knn_idx = reinterpret_cast<int*>(c->scratch.as<double>() + n * (size_t)k_list);
+    }
+    SE3_TRY(launch_knn_features(c->index[0].view, fa, c->stream));
+    return 0;
+}
+
+void identity_config(RunConfig& cfg, int variant, bool se3) {
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.entry = se3 ? SE3ICP_RUN_SE3_PURE : SE3ICP_RUN_ICP;
+    cfg.variant = variant;
+    cfg.max_iter = 1;
+    cfg.max_se3_iter = 1;
+    cfg.has_se3 = se3;
+    cfg.pure = se3;
+    cfg.alpha = 1.0;
+    cfg.beta = 1.0;
+    cfg.mse = 0;
+    cfg.mse_switch = 0;
+}
+
+int stage_state(se3icp_ctx* c) {
+    SE3_TRY(c->state.ensure(sizeof(IterState)));
+    SE3_TRY(c->hist.ensure(4 * 256 * sizeof(unsigned int)));
+    SE3_TRY(launch_init_state(c->dstate(), c->hist.as<unsigned int>(), c->stream));
+    return 0;
+}
+
+int stage_corr_alloc(se3icp_ctx* c, size_t n) {
+    SE3_TRY(c->corr_idx.ensure(n * sizeof(int)));
+    SE3_TRY(c->corr_dist.ensure(n * sizeof(double)));
+    SE3_TRY(c->corr_distf.ensure(n * sizeof(float)));
+    SE3_TRY(c->keep.ensure(n));
+    SE3_TRY(c->repair.ensure(n * sizeof(int)));
+    SE3_TRY(c->d2_nd.ensure(n * sizeof(double)));
+    SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, n * sizeof(int), c->stream));
+    return 0;
+}
+
+}  // namespace
+
+int se3icp_knn(se3icp_ctx* c, const double* xyz, size_t n, int k, int32_t* idx, double* d2) {
+    SE3_TRY(check_ctx(c));
+    if (!idx) return SE3ICP_ERR_ARG;
+    SE3_TRY(stage_features(c, xyz, n, 0, 0, k, true));
+    const double* dd = c->scratch.as<double>();
+    const int* di = reinterpret_cast<const int*>(dd + n * (size_t)k);
+    SE3_CUDA(cudaMemcpyAsync(idx, di, n * (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (d2) SE3_CUDA(cudaMemcpyAsync(d2, dd, n * (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return SE3ICP_OK;
+}
+
+int se3icp_lrf(se3icp_ctx* c, const double* xyz, size_t n, int k, double* frames) {
+    SE3_TRY(check_ctx(c));
+    if (!frames) return SE3ICP_ERR_ARG;
+    SE3_TRY(stage_features(c, xyz, n, k, 0, k, false));
+    std::vector<double> rows(9 * n);
+    SE3_TRY(download_planes(c, c->frame[0], rows.data(), n, 9));
+    for (size_t i = 0; i < n; i++) {
+        double* F = frames + 16 * i;
+        const double* r = &rows[9 * i];  // x-axis, y-axis, z-axis
+        for (int col = 0; col < 3; col++)
+            for (int row = 0; row < 3; row++) F[4 * row + col] = r[3 * col + row];
+        F[3] = xyz[3 * i], F[7] = xyz[3 * i + 1], F[11] = xyz[3 * i + 2];
+        F[12] = F[13] = F[14] = 0.0;
+        F[15] = 1.0;
+    }
+    return SE3ICP_OK;
+}
+
+int se3icp_normals(se3icp_ctx* c, const double* xyz, size_t n, int k, double* normals) {
+    SE3_TRY(check_ctx(c));
+    if (!normals) return SE3ICP_ERR_ARG;
+    SE3_TRY(stage_features(c, xyz, n, 0, k, k, false));
+    return download_planes(c, c->nrm[0], normals, n, 3);
+}
+
+int se3icp_gicp_cov(se3icp_ctx* c, const double* normals, size_t n, double eps, double* cov) {
+    SE3_TRY(check_ctx(c));
+    if (!normals || !cov || n == 0) return SE3ICP_ERR_ARG;
+    SE3_TRY(upload_planes(c, c->nrm[0], normals, n, 3, 3, 0));
+    SE3_TRY(c->cov[0].ensure(6 * n * sizeof(double)));
+    SE3_TRY(launch_cov_from_normals(c->nrm[0].as<double>(), (int)n, eps, c->cov[0].as<double>(), c->stream));
+    std::vector<double> c6(6 * n);
+    SE3_TRY(download_planes(c, c->cov[0], c6.data(), n, 6));
+    for (size_t i = 0; i < n; i++) {
+        const double* s = &c6[6 * i];
+        double* o = cov + 9 * i;
+        o[0] = s[0], o[1] = s[1], o[2] = s[2];
+        o[3] = s[1], o[4] = s[3], o[5] = s[4];
+        o[6] = s[2], o[7] = s[4], o[8] = s[5];
+    }
+    return SE3ICP_OK;
+}
+
+int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double* tgt_rows, size_t m, int nn_mode,
+                  int32_t* idx, double* d2, int64_t* exact_repairs) {
+    SE3_TRY(check_ctx(c));
+    if (!src_rows || !tgt_rows || !idx || n == 0 || m == 0) return SE3ICP_ERR_ARG;
+    // target: spatial order from the translation part, rotation planes as given (alpha = beta = 1)
+    std::vector<double> xyz(3 * m);
+    for (size_t j = 0; j < m; j++)
+        for (int k = 0; k < 3; k++) xyz[3 * j + k] = tgt_rows[12 * j + 9 + k];
+    SE3_TRY(upload_cloud_and_index(c, 1, xyz.data(), m));
+    SE3_TRY(upload_planes(c, c->frame[1], tgt_rows, m, 9, 12, 0));
+    SE3_TRY(c->rows32.ensure(3 * m * sizeof(float4)));
+    SE3_TRY(c->rows64.ensure(12 * m * sizeof(double)));
+    SE3_TRY(stage_state(c));
+    SE3_TRY(launch_pack_target_rows(c->index[1].view, c->frame[1].as<double>(), 1.0, 1.0, 0, c->rows32.as<float4>(),
+                                    c->rows64.as<double>(), c->dstate(), c->stream));
+    // source
+    SE3_TRY(upload_planes(c, c->frame[0], src_rows, n, 9, 12, 0));
+    SE3_TRY(upload_planes(c, c->scratch, src_rows, n, 3, 12, 9));
+    c->n[0] = n;
+    SourceView S{};
+    S.n = (int)n;
+    S.x = c->scratch.as<double>();
+    S.y = S.x + n;
+    S.z = S.x + 2 * n;
+    S.frame = c->frame[0].as<double>();
+    TargetView T = c->target_view();
+    RunConfig cfg;
+    identity_config(cfg, SE3ICP_PT2PT, true);
+    SE3_TRY(stage_corr_alloc(c, n));
+    CorrBuffers cb = c->corr_buffers(true);
+    switch (nn_mode) {
+        case SE3ICP_NN_AUTO:
+        case SE3ICP_NN_BRUTE_F32:
+            SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 0, c->stream));
+            break;
+        case SE3ICP_NN_EXACT_F64:
+            SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 1, c->stream));
+            break;
+        default:
+            set_last_error("nn_mode %d not available", nn_mode);
+            return SE3ICP_ERR_UNSUPPORTED;
+    }
+    SE3_TRY(launch_nn_se3_repair(S, T, cfg, c->dstate(), cb, c->stream));
+    SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaMemcpyAsync(idx, cb.idx, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (d2) SE3_CUDA(cudaMemcpyAsync(d2, cb.d2_nd, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    if (exact_repairs) *exact_repairs = c->h_state->repair_count;
+    return SE3ICP_OK;
+}
+
+int se3icp_nn_xyz(se3icp_ctx* c, const double* queries, size_t n, const double* tgt_xyz, size_t m, int32_t* idx,
+                  double* d2) {
+    SE3_TRY(check_ctx(c));
+    if (!queries || !tgt_xyz || !idx || n == 0 || m == 0) return SE3ICP_ERR_ARG;
+    SE3_TRY(upload_cloud_and_index(c, 1, tgt_xyz, m));
+    SE3_TRY(upload_planes(c, c->scratch, queries, n, 3, 3, 0));
+    SE3_TRY(stage_state(c));
+    c->n[0] = n;
+    SourceView S{};
+    S.n = (int)n;
+    S.x = c->scratch.as<double>();
+    S.y = S.x + n;
+    S.z = S.x + 2 * n;
+    TargetView T = c->target_view();
+    RunConfig cfg;
+    identity_config(cfg, SE3ICP_PT2PT, false);
+    SE3_TRY(stage_corr_alloc(c, n));
+    CorrBuffers cb = c->corr_buffers(true);
+    SE3_TRY(launch_nn_xyz(S, T, cfg, c->dstate(), cb, c->stream));
+    SE3_CUDA(cudaMemcpyAsync(idx, cb.idx, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (d2) SE3_CUDA(cudaMemcpyAsync(d2, cb.d2_nd, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return SE3ICP_OK;
+}
+
+int se3icp_trim(se3icp_ctx* c, const float* dist, size_t n, double overlap, int keep_largest, uint8_t* keep,
+                int64_t* n_keep) {
+    SE3_TRY(check_ctx(c));
+    if (!dist || !keep || n == 0) return SE3ICP_ERR_ARG;
+    SE3_TRY(stage_state(c));
+    SE3_TRY(stage_corr_alloc(c, n));
+    SE3_TRY(c->block_eq.ensure((size_t)kReduceBlocks * sizeof(int)));
+    SE3_CUDA(cudaMemcpyAsync(c->corr_distf.ptr, dist, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    RunConfig cfg;
+    identity_config(cfg, SE3ICP_PT2PT, false);
+    size_t k = std::min(trimmed_count(n, overlap), n);
+    cfg.trim_active = k < n;
+    cfg.n_keep_target = (int)k;
+    cfg.keep_largest = keep_largest != 0;
+    if (n_keep) *n_keep = (int64_t)k;
+    if (!cfg.trim_active) {  // pass-through branch of the rejector
+        memset(keep, 1, n);
+        return SE3ICP_OK;
+    }
+    if (k == 0) {
+        memset(keep, 0, n);
+        return SE3ICP_OK;
+    }
+    SE3_TRY(launch_trim(cfg, c->dstate(), c->corr_buffers(false), (int)n, c->hist.as<unsigned int>(),
+                        c->block_eq.as<int>(), c->stream));
+    SE3_CUDA(cudaMemcpyAsync(keep, c->keep.ptr, n, cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    return SE3ICP_OK;
+}
+
+namespace {
+
+// shared body of the three reduce entry points: uploads, runs reduce (+ optionally solve), returns sums
+int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* src_cov, size_t n, const double* tgt,
+                 const double* tgt_nrm, const double* tgt_cov, size_t m, const int32_t* corr_tgt, const double* conf_src,
+                 const double* conf_tgt, double* out27, double* T_out) {
+    if (!src || !tgt || !corr_tgt || n == 0 || m == 0) return SE3ICP_ERR_ARG;
+    SE3_TRY(upload_cloud_and_index(c, 1, tgt, m));
+    SE3_TRY(upload_planes(c, c->scratch, src, n, 3, 3, 0));
+    if (tgt_nrm) SE3_TRY(upload_planes(c, c->nrm[1], tgt_nrm, m, 3, 3, 0));
+    if (tgt_cov) SE3_TRY(upload_cov(c, c->cov[1], tgt_cov, m));
+    if (src_cov) SE3_TRY(upload_cov(c, c->cov[0], src_cov, n));
+    if (conf_src) SE3_TRY(upload_planes(c, c->conf[0], conf_src, n, 1, 1, 0));
+    if (conf_tgt) SE3_TRY(upload_planes(c, c->conf[1], conf_tgt, m, 1, 1, 0));
+    SE3_TRY(stage_state(c));
+    SE3_TRY(stage_corr_alloc(c, n));
+    SE3_CUDA(cudaMemcpyAsync(c->corr_idx.ptr, corr_tgt, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    SE3_CUDA(cudaMemsetAsync(c->corr_distf.ptr, 0, n * sizeof(float), c->stream));
+    SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));
+    c->n[0] = n;
+    SourceView S{};
+    S.n = (int)n;
+    S.x = c->scratch.as<double>();
+    S.y = S.x + n;
+    S.z = S.x + 2 * n;
+    S.cov = c->cov[0].as<double>();
+    S.conf = c->conf[0].as<double>();
+    TargetView T = c->target_view();
+    RunConfig cfg;
+    identity_config(cfg, variant, false);
+    cfg.with_cf = (conf_src && conf_tgt) ? 1 : 0;
+    SE3_TRY(launch_reduce(S, T, cfg, c->dstate(), c->corr_buffers(false), c->partials.as<double>(), c->stream));
+    if (out27) {
+        std::vector<double> part((size_t)kReduceBlocks * kReducePartials);
+        SE3_CUDA(cudaMemcpyAsync(part.data(), c->partials.ptr, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 27; k++) {
+            double s = 0.0;
+            for (int b = 0; b < kReduceBlocks; b++) s += part[(size_t)b * kReducePartials + k];
+            out27[k] = s;
+        }
+    }
+    if (T_out) {
+        SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), nullptr, c->hist.as<unsigned int>(), c->stream));
+        SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(T_out, c->h_state->T_i, 16 * sizeof(double));
+    }
+    return SE3ICP_OK;
+}
+
+}  // namespace
+
+int se3icp_reduce_pt2pt(se3icp_ctx* c, const double* src, size_t n, const double* tgt, size_t m, const int32_t* corr_tgt,
+                        double* T_out) {
+    SE3_TRY(check_ctx(c));
+    if (!T_out) return SE3ICP_ERR_ARG;
+    return stage_reduce(c, SE3ICP_PT2PT, src, nullptr, n, tgt, nullptr, nullptr, m, corr_tgt, nullptr, nullptr, nullptr, T_out);
+}
+
+int se3icp_reduce_pt2pl(se3icp_ctx* c, const double* src, size_t n, const double* tgt, const double* tgt_normals, size_t m,
+                        const int32_t* corr_tgt, double* out27) {
+    SE3_TRY(check_ctx(c));
+    if (!tgt_normals || !out27) return SE3ICP_ERR_ARG;
+    return stage_reduce(c, SE3ICP_PT2PL, src, nullptr, n, tgt, tgt_normals, nullptr, m, corr_tgt, nullptr, nullptr, out27,
+                        nullptr);
+}
+
+int se3icp_reduce_gicp(se3icp_ctx* c, const double* src, const double* src_cov, size_t n, const double* tgt,
+                       const double* tgt_cov, size_t m, const int32_t* corr_tgt, const double* conf_src,
+                       const double* conf_tgt, double* out27) {
+    SE3_TRY(check_ctx(c));
+    if (!src_cov || !tgt_cov || !out27) return SE3ICP_ERR_ARG;
+    return stage_reduce(c, SE3ICP_GICP, src, src_cov, n, tgt, nullptr, tgt_cov, m, corr_tgt, conf_src, conf_tgt, out27,
+                        nullptr);
+}
+
+int se3icp_solve(se3icp_ctx* c, const double* in27, double* T_out) {
+    SE3_TRY(check_ctx(c));
+    if (!in27 || !T_out) return SE3ICP_ERR_ARG;
+    SE3_TRY(stage_state(c));
+    SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));
+    std::vector<double> part((size_t)kReduceBlocks * kReducePartials, 0.0);
+    for (int k = 0; k < 27; k++) part[k] = in27[k];
+    part[28] = 1.0;  // one correspondence, so the solve is not skipped
+    SE3_CUDA(cudaMemcpyAsync(c->partials.ptr, part.data(), part.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RunConfig cfg;
+    identity_config(cfg, SE3ICP_PT2PL, false);
+    SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), nullptr, c->hist.as<unsigned int>(), c->stream));
+    SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(T_out, c->h_state->T_i, 16 * sizeof(double));
+    return SE3ICP_OK;
+}
+
+}  // extern "C"

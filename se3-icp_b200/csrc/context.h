@@ -1,0 +1,43 @@
+// context.h — the object behind se3icp_ctx: one stream, all device memory of one registration pair.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "index_storage.h"
+#include "internal.h"
+
+struct se3icp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // clouds as handed over by the caller (AoS doubles on the device)
+    se3::DeviceBuf raw[2];
+    const double* raw_view[2] = {nullptr, nullptr};  // raw[w].ptr, or a caller-owned device buffer
+    size_t n[2] = {0, 0};
+
+    se3::IndexStorage index[2];
+    se3::DeviceBuf frame[2], nrm[2], cov[2], conf[2];
+    se3::DeviceBuf rows32, rows64;
+    se3::DeviceBuf corr_idx, corr_dist, corr_distf, keep, repair, d2_nd;
+    se3::DeviceBuf psum[2], pmax[2];
+    se3::DeviceBuf partials, hist, block_eq, history;
+    se3::DeviceBuf state;
+    se3::DeviceBuf scratch;  // stage-level API staging
+
+    se3::IterState* h_state = nullptr;  // pinned
+    int* h_flag = nullptr;              // pinned
+    cudaEvent_t ev_begin = nullptr, ev_setup = nullptr, ev_end = nullptr;
+
+    se3::RunConfig cfg{};
+    se3icp_params params{};
+    bool run_pending = false;
+    bool variant_valid = true;
+    long long launches = 0;
+    int history_capacity = 0;
+
+    se3::IterState* dstate() const { return state.as<se3::IterState>(); }
+    se3::SourceView source_view() const;
+    se3::TargetView target_view() const;
+    se3::CorrBuffers corr_buffers(bool with_d2) const;
+};

@@ -1,0 +1,39 @@
+// index_storage.h — grow-only device buffers and the owner of one cloud's spatial index.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "internal.h"
+
+namespace se3 {
+
+struct DeviceBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    DeviceBuf() = default;
+    DeviceBuf(const DeviceBuf&) = delete;
+    DeviceBuf& operator=(const DeviceBuf&) = delete;
+    ~DeviceBuf() { release(); }
+    // grow-only; contents are NOT preserved across a growth
+    int ensure(size_t bytes);
+    // grow-only and preserving the first `keep` bytes (used by append)
+    int ensure_keep(size_t bytes, size_t keep, cudaStream_t st);
+    void release();
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(ptr);
+    }
+};
+
+struct IndexStorage {
+    CloudIndex view;
+    DeviceBuf x, y, z, sx, sy, sz, perm, keys, keys_tmp, vals_tmp, box, bbox, bbox_part, sort_tmp;
+    size_t sort_tmp_bytes = 0;
+    void plan_levels(int n);
+    int reserve(int n);
+    int build(cudaStream_t st, long long* launches);
+};
+
+}  // namespace se3

@@ -1,0 +1,171 @@
+// internal.h — device-side data layout and kernel launchers shared by the .cu files.
+//
+// HBM layout (per cloud, working frame = normalised coordinates for the SE(3) entries, raw for run_icp):
+//   x,y,z        FP64 SoA, ORIGINAL point order            (gathers by correspondence index)
+//   sx,sy,sz     FP64 SoA, MORTON order                    (coalesced leaf loads in the traversals)
+//   perm         int32  morton position -> original index
+//   keys         uint64 sorted 63-bit Morton codes
+//   box          float  [6][nodes] outward-rounded AABBs of the implicit 32-wide hierarchy
+//                (level 0 = leaves of 32 consecutive Morton points, level l+1 = 32 nodes of level l)
+//   frame        FP64 [9][n]  TOLDI rotation, 12-vector order (x-axis, y-axis, z-axis), original order
+//   nrm / cov    FP64 [3][n] / [6][n] (symmetric packing 00,01,02,11,12,22), original order
+//   rows32       float4 [3][n] 12-float SE(3) rows (alpha R | beta p), MORTON order   (brute-force tiles)
+//   rows64       FP64 [12][n] same rows, MORTON order                                  (exact evaluation)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/se3icp.h"
+
+namespace se3 {
+
+constexpr int kMaxLevels = 8;
+constexpr int kReducePartials = 32;  // doubles per block partial record
+constexpr int kReduceBlocks = 296;   // 2 x 148 SMs: fixed grid -> deterministic partial layout
+
+struct CloudIndex {
+    int n = 0;
+    int n_levels = 0;
+    int total_nodes = 0;
+    int level_off[kMaxLevels] = {0};
+    int level_cnt[kMaxLevels] = {0};
+    const double* x = nullptr;
+    const double* y = nullptr;
+    const double* z = nullptr;
+    const double* sx = nullptr;
+    const double* sy = nullptr;
+    const double* sz = nullptr;
+    const int* perm = nullptr;
+    const uint64_t* keys = nullptr;
+    const float* box = nullptr;     // [6][total_nodes]
+    const double* bbox = nullptr;   // device: lo[3], hi[3] of the cloud (for Morton quantisation)
+};
+
+// Everything the iteration kernels need that changes on the device between iterations.
+struct IterState {
+    double T_total[16];
+    double T_prev[16];
+    double T_i[16];
+    double T_final[16];
+    double c_src[3];
+    double c_tgt[3];
+    double scale;
+    double mse_prev, mse_cur, mse_rel, T_change;
+    double tgt_absmax;  // max |coordinate| over the target SE(3) rows (certification bound)
+    int iter;
+    int se3_iters;
+    int switch_icp;
+    int done;
+    int n_keep;
+    unsigned int thr_bits;
+    int eq_budget;
+    int repair_count;
+    int hist_count;
+    int pad0;
+    long long total_repairs;
+    unsigned long long t_mark;      // globaltimer at the end of the previous solve/update
+    unsigned long long t_corr_ns;   // accumulated correspondence-search time
+    unsigned long long t_start;     // globaltimer at state initialisation
+    unsigned long long t_switch;    // globaltimer when the ICP phase began
+};
+
+// Fixed (per run) configuration passed by value to the kernels.
+struct RunConfig {
+    int entry;
+    int variant;
+    int max_iter;
+    int max_se3_iter;
+    int has_se3;      // entry != RUN_ICP
+    int pure;         // entry == RUN_SE3_PURE
+    int with_cf;      // entry == RUN_SE3_ICP_CF
+    int trim_active;  // floor(float(overlap) * N) < N
+    int n_keep_target;
+    int keep_largest;
+    int record_history;
+    int max_history;
+    double mse;
+    double mse_switch;
+    double alpha;
+    double beta;
+};
+
+struct SourceView {
+    int n;
+    const double* x;      // working-frame original coordinates p0 (never rewritten: q = T_total * p0 on the fly)
+    const double* y;
+    const double* z;
+    const double* frame;  // [9][n]
+    const double* cov;    // [6][n] or null
+    const double* conf;   // [n] or null
+};
+
+struct TargetView {
+    int n;
+    CloudIndex idx;
+    const double* nrm;    // [3][n] or null
+    const double* cov;    // [6][n] or null
+    const double* conf;   // [n] or null
+    const float4* rows32; // [3][n] morton order
+    const double* rows64; // [12][n] morton order
+    const float* box12;   // [24][total_nodes] 12-D boxes for the pruned SE(3) search (or null)
+};
+
+struct CorrBuffers {
+    double* d2_nd;   // optional [N] squared distance in the search space (12-D or 3-D), stage API
+    int* idx;        // [N] matched target (original index), persists across iterations (warm start)
+    double* dist;    // [N] FP64 distance (reference distances_vec)
+    float* distf;    // [N] stored float distance (pcl::Correspondence::distance)
+    uint8_t* keep;   // [N] trim mask (valid when trim_active)
+    int* repair;     // [N] queries needing the exact FP64 repair
+};
+
+// ---- launchers (all asynchronous on `st`) ------------------------------------------------------
+// spatial_index.cu
+struct IndexStorage;  // owns the buffers behind a CloudIndex
+int launch_sum_xyz(const double* aos, int n, double* partial /*[kReduceBlocks*3]*/, cudaStream_t st);
+int launch_maxdist(const double* aos, int n, const double* partial_sum, double* partial_max /*[kReduceBlocks]*/,
+                   cudaStream_t st);
+int launch_normalise(const double* aos, int n, const double* psum_self, const double* pmax_src,
+                     const double* pmax_tgt, int n_src, int n_tgt, double scale_pre, int which, IterState* state,
+                     double* x, double* y, double* z, cudaStream_t st);
+int launch_aos_to_soa(const double* aos, int n, double* x, double* y, double* z, cudaStream_t st);
+int launch_confidence(const double* aos, int n, double* conf, cudaStream_t st);
+
+// knn_features.cu
+struct FeatureArgs {
+    int k_lrf;        // 0 = no LRF
+    int k_nrm;        // 0 = no normals
+    int want_cov;     // GICP covariance from the normal
+    double gicp_eps;
+    double* frame;    // [9][n]
+    double* nrm;      // [3][n]
+    double* cov;      // [6][n]
+    int* knn_idx;     // optional [n*K] (stage API), original order rows
+    double* knn_d2;   // optional [n*K]
+    int K;            // list length = max(k_lrf, k_nrm, requested)
+};
+int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t st);
+int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, double* cov /*[6][n]*/, cudaStream_t st);
+
+// nn_search.cu
+int launch_pack_target_rows(const CloudIndex& I, const double* frame, double alpha, double beta, int cf_unscaled_p,
+                            float4* rows32, double* rows64, IterState* state, cudaStream_t st);
+int launch_nn_se3_brute(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,
+                        CorrBuffers cb, int force_all_repair, cudaStream_t st);
+int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,
+                         CorrBuffers cb, cudaStream_t st);
+int launch_nn_xyz(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                  cudaStream_t st);
+
+// optimise.cu
+int launch_trim(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, unsigned int* hist /*[4*256]*/,
+                int* block_eq /*[kReduceBlocks]*/, cudaStream_t st);
+int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                  double* partials /*[kReduceBlocks*kReducePartials]*/, cudaStream_t st);
+int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, double* history,
+                        unsigned int* hist /*[4*256] trim histograms, zeroed for the next iteration*/, cudaStream_t st);
+int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st);
+int launch_init_state(IterState* state, unsigned int* hist, cudaStream_t st);
+
+}  // namespace se3

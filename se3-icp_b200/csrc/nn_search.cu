@@ -1,0 +1,363 @@
+// nn_search.cu — correspondence search.
+//
+//  * pack_target_rows   reference .cpp:597-626: alpha/beta weighting and the 12 x M data matrix, stored
+//                       in Morton order as float4 tiles (sweep) and FP64 planes (exact evaluation).
+//  * nn_se3_brute       reference .cpp:444-470 (update_correspondences_raw_flann_SE3): tiled FP32
+//                       sweep with top-2 tracking and a rigorous certification test; the query is
+//                       T_total * X0 formed on the fly (the reference's rewrite of source_se3_cloud_,
+//                       .cpp:713-716, is fused away).
+//  * nn_se3_repair      exact FP64 sweep for the queries the FP32 pass could not certify
+//                       (also the whole search in SE3ICP_NN_EXACT_F64 mode).
+//  * nn_xyz             reference .cpp:402-416 (update_correspondences_kd_tree_XYZ): warp-per-query
+//                       pruned traversal, FP64, warm-started from the previous correspondence.
+// Ties resolve to the smallest original index (the oracle's rule).
+#include "common.cuh"
+#include "internal.h"
+#include "morton.cuh"
+#include "traverse.cuh"
+
+namespace se3 {
+
+__device__ __forceinline__ bool se3_phase_active(const RunConfig& cfg, const IterState* st) {
+    return cfg.has_se3 && (cfg.pure || !st->switch_icp);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_target_rows_kernel(CloudIndex I, const double* __restrict__ frame, double alpha,
+                                                                double beta, int cf_unscaled_p, float4* __restrict__ rows32,
+                                                                double* __restrict__ rows64, IterState* __restrict__ state) {
+    const size_t n = (size_t)I.n;
+    double amax = 0.0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < I.n; s += gridDim.x * blockDim.x) {
+        int o = I.perm[s];
+        double v[12];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v[k] = frame[k * n + o] * alpha;  // .cpp:605
+        double px = I.sx[s], py = I.sy[s], pz = I.sz[s];
+        // .cpp:606 (beta) — run_se3_icp_with_cf feeds the tree the unscaled point (.cpp:834-836)
+        v[9] = cf_unscaled_p ? px : px * beta;
+        v[10] = cf_unscaled_p ? py : py * beta;
+        v[11] = cf_unscaled_p ? pz : pz * beta;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            rows64[k * n + s] = v[k];
+            amax = fmax(amax, fabs(v[k]));
+        }
+        rows32[s] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        rows32[n + s] = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+        rows32[2 * n + s] = make_float4((float)v[8], (float)v[9], (float)v[10], (float)v[11]);
+    }
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.0)
+        atomicMax(reinterpret_cast<unsigned long long*>(&state->tgt_absmax), (unsigned long long)__double_as_longlong(amax));
+}
+
+int launch_pack_target_rows(const CloudIndex& I, const double* frame, double alpha, double beta, int cf_unscaled_p,
+                            float4* rows32, double* rows64, IterState* state, cudaStream_t st) {
+    int g = (I.n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    pack_target_rows_kernel<<<g, 256, 0, st>>>(I, frame, alpha, beta, cf_unscaled_p, rows32, rows64, state);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// query i: 12-vector of T_total * [alpha R0 | beta p0]  (reference .cpp:450-453 after .cpp:713-716)
+__device__ __forceinline__ void make_query(const SourceView& S, const RunConfig& cfg, const double* __restrict__ Tm, int i,
+                                           double q[12]) {
+    const size_t n = (size_t)S.n;
+    double R0[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R0[k] = S.frame[k * n + i] * cfg.alpha;
+    double p[3] = {S.x[i] * cfg.beta, S.y[i] * cfg.beta, S.z[i] * cfg.beta};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {  // column c of the rotation block
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            q[3 * c + r] = Tm[4 * r] * R0[3 * c] + Tm[4 * r + 1] * R0[3 * c + 1] + Tm[4 * r + 2] * R0[3 * c + 2];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) q[9 + r] = Tm[4 * r] * p[0] + Tm[4 * r + 1] * p[1] + Tm[4 * r + 2] * p[2] + Tm[4 * r + 3];
+}
+
+// exact FP64 squared distance between a query and Morton row j (sequential, non-contracted)
+__device__ __forceinline__ double exact_d2_12(const double q[12], const double* __restrict__ rows64, size_t m, int j) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        double df = __dsub_rn(q[k], rows64[k * m + j]);
+        s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    return s;
+}
+
+__device__ __forceinline__ void write_se3_match(const TargetView& T, const RunConfig& cfg, CorrBuffers& cb, int i,
+                                                const double q[12], int j, double d2_12) {
+    const size_t m = (size_t)T.n;
+    // reference .cpp:465-467: stored distance is the 3-D distance of the translation columns
+    // (target_se3_cloud_ column = beta * p even in the _with_cf variant)
+    double tx = T.idx.sx[j] * cfg.beta, ty = T.idx.sy[j] * cfg.beta, tz = T.idx.sz[j] * cfg.beta;
+    (void)m;
+    double d3 = sqrt(sqdist3(q[9], q[10], q[11], tx, ty, tz));
+    cb.idx[i] = T.idx.perm[j];
+    cb.dist[i] = d3;
+    cb.distf[i] = (float)d3;
+    if (cb.d2_nd) cb.d2_nd[i] = d2_12;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kBfThreads = 128;
+constexpr int kBfQ = 2;       // queries per thread
+constexpr int kBfTile = 256;  // target rows per shared-memory tile
+
+__global__ void __launch_bounds__(kBfThreads) nn_se3_brute_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                                    IterState* __restrict__ state, CorrBuffers cb,
+                                                                    int force_all) {
+    if (state->done || !se3_phase_active(cfg, state)) return;
+    __shared__ float4 tile[3][kBfTile];
+    __shared__ double Tm[16];
+    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
+    __syncthreads();
+
+    const int M = T.n;
+    float qf[kBfQ][12];
+    float b1[kBfQ], b2[kBfQ];
+    int i1[kBfQ];
+    int qi[kBfQ];
+#pragma unroll
+    for (int u = 0; u < kBfQ; u++) {
+        qi[u] = blockIdx.x * (kBfThreads * kBfQ) + u * kBfThreads + threadIdx.x;
+        b1[u] = b2[u] = 3.0e38f;
+        i1[u] = 0;
+        if (qi[u] < S.n) {
+            double q[12];
+            make_query(S, cfg, Tm, qi[u], q);
+#pragma unroll
+            for (int k = 0; k < 12; k++) qf[u][k] = (float)q[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; k++) qf[u][k] = 0.f;
+        }
+    }
+
+    for (int base = 0; base < M; base += kBfTile) {
+        for (int t = threadIdx.x; t < 3 * kBfTile; t += kBfThreads) {
+            int plane = t / kBfTile, j = t - plane * kBfTile;
+            int g = base + j;
+            tile[plane][j] = g < M ? T.rows32[(size_t)plane * M + g] : make_float4(1e15f, 1e15f, 1e15f, 1e15f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < kBfTile; j++) {
+            float4 a = tile[0][j], b = tile[1][j], c = tile[2][j];
+#pragma unroll
+            for (int u = 0; u < kBfQ; u++) {
+                float e, d;
+                e = qf[u][0] - a.x;  d = e * e;
+                e = qf[u][1] - a.y;  d = fmaf(e, e, d);
+                e = qf[u][2] - a.z;  d = fmaf(e, e, d);
+                e = qf[u][3] - a.w;  d = fmaf(e, e, d);
+                e = qf[u][4] - b.x;  d = fmaf(e, e, d);
+                e = qf[u][5] - b.y;  d = fmaf(e, e, d);
+                e = qf[u][6] - b.z;  d = fmaf(e, e, d);
+                e = qf[u][7] - b.w;  d = fmaf(e, e, d);
+                e = qf[u][8] - c.x;  d = fmaf(e, e, d);
+                e = qf[u][9] - c.y;  d = fmaf(e, e, d);
+                e = qf[u][10] - c.z; d = fmaf(e, e, d);
+                e = qf[u][11] - c.w; d = fmaf(e, e, d);
+                b2[u] = fminf(b2[u], fmaxf(d, b1[u]));
+                i1[u] = d < b1[u] ? base + j : i1[u];
+                b1[u] = fminf(b1[u], d);
+            }
+        }
+        __syncthreads();
+    }
+
+    const double tgt_absmax = state->tgt_absmax;
+#pragma unroll
+    for (int u = 0; u < kBfQ; u++) {
+        int i = qi[u];
+        if (i >= S.n) continue;
+        double q[12];
+        make_query(S, cfg, Tm, i, q);
+        double amax = 0.0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) amax = fmax(amax, fabs(q[k]));
+        // |s - d2| <= eps(s): FP32 rounding of the 24 inputs (delta per coordinate difference) plus
+        // the rounding of the 24 FP32 operations; generous constants, see DESIGN.md "certification".
+        double delta = (amax + tgt_absmax) * 5.9604644775390625e-08;  // 2^-24
+        double s1 = b1[u], s2 = b2[u];
+        double e1 = s1 * 1.9073486328125e-06 + 8.0 * delta * sqrt(s1) + 16.0 * delta * delta;
+        double e2 = s2 * 1.9073486328125e-06 + 8.0 * delta * sqrt(s2) + 16.0 * delta * delta;
+        bool certified = !force_all && (s2 - e2 > s1 + e1);
+        if (certified) {
+            write_se3_match(T, cfg, cb, i, q, i1[u], cb.d2_nd ? exact_d2_12(q, T.rows64, (size_t)M, i1[u]) : 0.0);
+        } else {
+            int pos = atomicAdd(&state->repair_count, 1);
+            cb.repair[pos] = i;
+        }
+    }
+}
+
+int launch_nn_se3_brute(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                        int force_all_repair, cudaStream_t st) {
+    int per_block = kBfThreads * kBfQ;
+    int g = (S.n + per_block - 1) / per_block;
+    nn_se3_brute_kernel<<<g, kBfThreads, 0, st>>>(S, T, cfg, state, cb, force_all_repair);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kRepairThreads = 256;
+
+__global__ void __launch_bounds__(kRepairThreads) nn_se3_repair_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                                        IterState* __restrict__ state, CorrBuffers cb) {
+    if (state->done || !se3_phase_active(cfg, state)) return;
+    __shared__ double Tm[16];
+    __shared__ double sd[kRepairThreads / 32];
+    __shared__ int sid[kRepairThreads / 32];
+    __shared__ int sj[kRepairThreads / 32];
+    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
+    __syncthreads();
+    const int count = state->repair_count;
+    const int M = T.n;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int r = blockIdx.x; r < count; r += gridDim.x) {
+        const int i = cb.repair[r];
+        double q[12];
+        make_query(S, cfg, Tm, i, q);
+        double best = inf;
+        int best_id = 0x7fffffff, best_j = 0;
+        for (int j = threadIdx.x; j < M; j += kRepairThreads) {
+            double d2 = exact_d2_12(q, T.rows64, (size_t)M, j);
+            if (d2 < best) {
+                best = d2;
+                best_j = j;
+                best_id = T.idx.perm[j];
+            } else if (d2 == best) {
+                int id = T.idx.perm[j];
+                if (id < best_id) {
+                    best_id = id;
+                    best_j = j;
+                }
+            }
+        }
+        // block argmin on (d2, original id)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_xor_sync(SE3_FULL, best, o);
+            int oi = __shfl_xor_sync(SE3_FULL, best_id, o);
+            int oj = __shfl_xor_sync(SE3_FULL, best_j, o);
+            if (od < best || (od == best && oi < best_id)) {
+                best = od;
+                best_id = oi;
+                best_j = oj;
+            }
+        }
+        int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) {
+            sd[w] = best;
+            sid[w] = best_id;
+            sj[w] = best_j;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < kRepairThreads / 32; k++) {
+                if (sd[k] < best || (sd[k] == best && sid[k] < best_id)) {
+                    best = sd[k];
+                    best_id = sid[k];
+                    best_j = sj[k];
+                }
+            }
+            write_se3_match(T, cfg, cb, i, q, best_j, best);
+        }
+        __syncthreads();
+    }
+}
+
+int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                         cudaStream_t st) {
+    int g = S.n < 148 * 4 ? (S.n > 0 ? S.n : 1) : 148 * 4;
+    nn_se3_repair_kernel<<<g, kRepairThreads, 0, st>>>(S, T, cfg, state, cb);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kXyzWarps = 8;
+
+__global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                                 IterState* __restrict__ state, CorrBuffers cb) {
+    if (state->done || se3_phase_active(cfg, state)) return;
+    __shared__ int2 stacks[kXyzWarps][kStackEntries];
+    __shared__ double Tm[16];
+    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * kXyzWarps + wib;
+    if (i >= S.n) return;
+    const CloudIndex& I = T.idx;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    // source_moving_ point: T_total * p0 (the reference re-transforms the cloud every iteration, .cpp:541,706)
+    const double px = S.x[i], py = S.y[i], pz = S.z[i];
+    const double qx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3];
+    const double qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
+    const double qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
+
+    double tau = inf;
+    int best = 0x7fffffff;
+    auto leaf_fn = [&](int leaf) {
+        int p = leaf * 32 + lane;
+        double d2 = inf;
+        int id = 0x7fffffff;
+        if (p < I.n) {
+            d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
+            id = I.perm[p];
+        }
+        warp_argmin(d2, id);
+        if (d2 < tau || (d2 == tau && id < best)) {
+            tau = d2;
+            best = id;
+        }
+    };
+
+    int prev = cb.idx[i];
+    if (prev >= 0 && prev < I.n) {
+        tau = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
+        best = prev;
+    } else {
+        // no warm start: the leaf holding the query's Morton code gives the first radius
+        uint64_t key = morton63(qx, qy, qz, I.bbox);
+        int lo = 0, hi = I.n;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (I.keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= I.n) lo = I.n - 1;
+        leaf_fn(lo >> 5);
+    }
+    traverse_boxes(I, qx, qy, qz, tau, stacks[wib], lane, leaf_fn);
+
+    if (lane == 0) {
+        double d = sqrt(tau);  // .cpp:411
+        cb.idx[i] = best;
+        cb.dist[i] = d;
+        cb.distf[i] = (float)d;  // .cpp:413
+        if (cb.d2_nd) cb.d2_nd[i] = tau;
+    }
+}
+
+int launch_nn_xyz(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                  cudaStream_t st) {
+    if (T.idx.n_levels > 6) {
+        set_last_error("cloud too large for the traversal stack");
+        return SE3ICP_ERR_UNSUPPORTED;
+    }
+    int g = (S.n + kXyzWarps - 1) / kXyzWarps;
+    nn_xyz_kernel<<<g, kXyzWarps * 32, 0, st>>>(S, T, cfg, state, cb);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se3

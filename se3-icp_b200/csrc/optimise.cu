@@ -1,0 +1,649 @@
+// optimise.cu — trimmed rejection, normal-equation reduction, on-device solve and loop control
+// (SURVEY §8 a9-a18).
+//
+//  * trim_*          PCL CorrespondenceRejectorTrimmed (reference .cpp:634-635,669-671): radix-select of
+//                    the n_keep-th float distance, ties at the threshold kept in index order.
+//  * reduce          one fused gather + residual/Jacobian + FP64 accumulation pass per iteration for
+//                    pt2pt (Umeyama sums, reference .cpp:692), pt2pl (.cpp:695) and GICP (.cpp:57-110,
+//                    698, with the confidence weights of .cpp:913 for run_se3_icp_with_cf).  The source
+//                    point and its covariance are T_total * p0 and R C0 R^T formed on the fly, so the
+//                    reference's Transform() pass (.cpp:706) never touches memory.
+//  * solve_update    fixed-order sum of the per-block partials, 6x6 LDL^T solve or 3x3 Kabsch, Euler
+//                    update, T accumulation, mean-distance bookkeeping and the phase / stop logic of
+//                    .cpp:709-729 (run_icp: .cpp:544-550, run_se3_pure: .cpp:1118), all on the device.
+#include "common.cuh"
+#include "internal.h"
+
+namespace se3 {
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ bool se3_phase_active_o(const RunConfig& cfg, const IterState* st) {
+    return cfg.has_se3 && (cfg.pure || !st->switch_icp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+__global__ void init_state_kernel(IterState* st, unsigned int* hist) {
+    int t = threadIdx.x;
+    if (t < 16) {
+        double v = (t % 5 == 0) ? 1.0 : 0.0;
+        st->T_total[t] = v;
+        st->T_prev[t] = v;
+        st->T_i[t] = v;
+        st->T_final[t] = v;
+    }
+    if (t == 0) {
+        for (int k = 0; k < 3; k++) st->c_src[k] = st->c_tgt[k] = 0.0;
+        st->scale = 1.0;
+        st->mse_prev = st->mse_cur = st->mse_rel = 10000000.0;  // reference .cpp:485,631
+        st->T_change = 10000000.0;
+        st->tgt_absmax = 0.0;
+        st->iter = 0;
+        st->se3_iters = 0;
+        st->switch_icp = 0;
+        st->done = 0;
+        st->n_keep = 0;
+        st->thr_bits = 0;
+        st->eq_budget = 0;
+        st->repair_count = 0;
+        st->hist_count = 0;
+        st->total_repairs = 0;
+        st->t_corr_ns = 0;
+        st->t_start = global_timer_ns();
+        st->t_mark = st->t_start;
+        st->t_switch = 0;
+    }
+    if (hist)
+        for (int k = t; k < 4 * 256; k += blockDim.x) hist[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trimmed rejection
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int trim_key(float d, int keep_largest) {
+    unsigned int b = __float_as_uint(d);
+    return keep_largest ? ~b : b;
+}
+
+// warp-cooperative: bin holding rank k in a 256-bin histogram; k becomes the rank inside that bin
+__device__ __forceinline__ int warp_select_bin(const unsigned int* __restrict__ hist, unsigned int& k, int lane) {
+    unsigned int loc[8], sum = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        loc[e] = hist[lane * 8 + e];
+        sum += loc[e];
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int v = __shfl_up_sync(SE3_FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    unsigned int excl = incl - sum;
+    bool mine = (k >= excl) && (k < incl);
+    unsigned int m = __ballot_sync(SE3_FULL, mine);
+    int owner = m ? (__ffs(m) - 1) : 31;
+    int bin = 0;
+    unsigned int krem = 0;
+    if (lane == owner) {
+        unsigned int c = excl;
+        bin = lane * 8 + 7;
+        krem = 0;
+        for (int e = 0; e < 8; e++) {
+            if (k < c + loc[e]) {
+                bin = lane * 8 + e;
+                krem = k - c;
+                break;
+            }
+            c += loc[e];
+        }
+    }
+    bin = __shfl_sync(SE3_FULL, bin, owner);
+    k = __shfl_sync(SE3_FULL, krem, owner);
+    return bin;
+}
+
+// chain of selections for passes [0, upto): returns the key prefix (high digits) and the remaining rank
+__device__ __forceinline__ void trim_prefix(const unsigned int* __restrict__ hist, int upto, unsigned int k0, int lane,
+                                            unsigned int& prefix, unsigned int& krem) {
+    prefix = 0;
+    krem = k0;
+    for (int p = 0; p < upto; p++) {
+        int bin = warp_select_bin(hist + p * 256, krem, lane);
+        prefix |= (unsigned int)bin << (24 - 8 * p);
+    }
+}
+
+__global__ void __launch_bounds__(256) trim_hist_kernel(RunConfig cfg, const IterState* __restrict__ state,
+                                                         const float* __restrict__ distf, int n, unsigned int* __restrict__ hist,
+                                                         int pass) {
+    if (state->done) return;
+    __shared__ unsigned int sh[256];
+    __shared__ unsigned int s_prefix;
+    sh[threadIdx.x] = 0;
+    if (threadIdx.x < 32) {
+        unsigned int prefix, krem;
+        trim_prefix(hist, pass, (unsigned int)(cfg.n_keep_target - 1), threadIdx.x, prefix, krem);
+        if (threadIdx.x == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const int shift = 24 - 8 * pass;
+    const unsigned int himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned int key = trim_key(distf[i], cfg.keep_largest);
+        if ((key & himask) == prefix) atomicAdd(&sh[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    unsigned int v = sh[threadIdx.x];
+    if (v) atomicAdd(&hist[pass * 256 + threadIdx.x], v);
+}
+
+// chunked, order-preserving: block b owns elements [b*chunk, (b+1)*chunk)
+__global__ void __launch_bounds__(256) trim_count_eq_kernel(RunConfig cfg, const IterState* __restrict__ state,
+                                                             const float* __restrict__ distf, int n,
+                                                             const unsigned int* __restrict__ hist, int* __restrict__ block_eq) {
+    if (state->done) return;
+    __shared__ unsigned int s_thr;
+    __shared__ int s_cnt[8];
+    if (threadIdx.x < 32) {
+        unsigned int prefix, krem;
+        trim_prefix(hist, 4, (unsigned int)(cfg.n_keep_target - 1), threadIdx.x, prefix, krem);
+        if (threadIdx.x == 0) s_thr = prefix;
+    }
+    __syncthreads();
+    const unsigned int thr = s_thr;
+    int chunk = (n + gridDim.x - 1) / gridDim.x;
+    int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    int c = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) c += trim_key(distf[i], cfg.keep_largest) == thr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(SE3_FULL, c, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; k++) t += s_cnt[k];
+        block_eq[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) trim_apply_kernel(RunConfig cfg, IterState* __restrict__ state,
+                                                          const float* __restrict__ distf, int n,
+                                                          const unsigned int* __restrict__ hist, const int* __restrict__ block_eq,
+                                                          uint8_t* __restrict__ keep) {
+    if (state->done) return;
+    __shared__ unsigned int s_thr, s_budget;
+    __shared__ int s_base;
+    __shared__ int s_warp[8];
+    if (threadIdx.x < 32) {
+        unsigned int prefix, krem;
+        trim_prefix(hist, 4, (unsigned int)(cfg.n_keep_target - 1), threadIdx.x, prefix, krem);
+        if (threadIdx.x == 0) {
+            s_thr = prefix;
+            s_budget = krem + 1;  // how many of the elements equal to the threshold survive
+            int base = 0;
+            for (int b = 0; b < (int)blockIdx.x; b++) base += block_eq[b];
+            s_base = base;
+            if (blockIdx.x == 0) {
+                state->thr_bits = prefix;
+                state->eq_budget = (int)(krem + 1);
+                state->n_keep = cfg.n_keep_target;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int thr = s_thr;
+    const int budget = (int)s_budget;
+    int running = s_base;
+    int chunk = (n + gridDim.x - 1) / gridDim.x;
+    int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = lo; base < hi; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        unsigned int key = i < hi ? trim_key(distf[i], cfg.keep_largest) : 0xffffffffu;
+        bool eq = i < hi && key == thr;
+        unsigned int m = __ballot_sync(SE3_FULL, eq);
+        int in_warp = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[w] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < 8; k++) {
+            if (k < w) before += s_warp[k];
+            total += s_warp[k];
+        }
+        if (i < hi) keep[i] = (key < thr) || (eq && (running + before + in_warp) < budget);
+        running += total;
+        __syncthreads();
+    }
+}
+
+int launch_trim(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, unsigned int* hist, int* block_eq,
+                cudaStream_t st) {
+    if (!cfg.trim_active) return 0;
+    int g = (n + 255) / 256;
+    if (g > 148 * 4) g = 148 * 4;
+    for (int pass = 0; pass < 4; pass++) trim_hist_kernel<<<g, 256, 0, st>>>(cfg, state, cb.distf, n, hist, pass);
+    trim_count_eq_kernel<<<kReduceBlocks, 256, 0, st>>>(cfg, state, cb.distf, n, hist, block_eq);
+    trim_apply_kernel<<<kReduceBlocks, 256, 0, st>>>(cfg, state, cb.distf, n, hist, block_eq, cb.keep);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduction.  Partial record (kReducePartials doubles per block):
+//   pt2pl / gicp : [0..20] upper triangle of JTJ (row-major), [21..26] JTr
+//   pt2pt        : [0..2] sum(s-a), [3..5] sum(t-b), [6..14] sum (t-b)(s-a)^T row-major
+//   all          : [27] sum of distances, [28] count, [29] first-block start time marker (unused)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAcc = 29;
+
+__global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T, RunConfig cfg, IterState* __restrict__ state,
+                                                      CorrBuffers cb, double* __restrict__ partials) {
+    if (state->done) return;
+    __shared__ double Tm[16];
+    __shared__ double sm[8][kAcc];
+    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // correspondence search of this iteration ended when this kernel started
+        unsigned long long now = global_timer_ns();
+        state->t_corr_ns += now - state->t_mark;
+    }
+    __syncthreads();
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
+
+    const size_t n = (size_t)S.n, m = (size_t)T.n;
+    // reference points that keep the pt2pt sums well conditioned (exact algebra for any a, b)
+    double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+    if (cfg.variant == SE3ICP_PT2PT) {
+        double c0x = cfg.has_se3 ? 0.0 : state->c_src[0], c0y = cfg.has_se3 ? 0.0 : state->c_src[1],
+               c0z = cfg.has_se3 ? 0.0 : state->c_src[2];
+        ax = Tm[0] * c0x + Tm[1] * c0y + Tm[2] * c0z + Tm[3];
+        ay = Tm[4] * c0x + Tm[5] * c0y + Tm[6] * c0z + Tm[7];
+        az = Tm[8] * c0x + Tm[9] * c0y + Tm[10] * c0z + Tm[11];
+        if (!cfg.has_se3) {
+            bx = state->c_tgt[0];
+            by = state->c_tgt[1];
+            bz = state->c_tgt[2];
+        }
+    }
+
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) {
+        if (cfg.trim_active && !cb.keep[i]) continue;
+        const int j = cb.idx[i];
+        if (j < 0) continue;
+        const double px = S.x[i], py = S.y[i], pz = S.z[i];
+        const double sx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3];
+        const double sy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
+        const double sz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
+        const double tx = T.idx.x[j], ty = T.idx.y[j], tz = T.idx.z[j];
+        const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
+        acc[28] += 1.0;
+        if (cfg.with_cf)
+            acc[27] += sqrt(dx * dx + dy * dy + dz * dz);  // .cpp:396 recomputed in double
+        else
+            acc[27] += (double)cb.distf[i];  // .cpp:383 stored float distance
+
+        if (cfg.variant == SE3ICP_PT2PT) {
+            double us = sx - ax, vs = sy - ay, ws = sz - az;
+            double ut = tx - bx, vt = ty - by, wt = tz - bz;
+            acc[0] += us, acc[1] += vs, acc[2] += ws;
+            acc[3] += ut, acc[4] += vt, acc[5] += wt;
+            acc[6] += ut * us, acc[7] += ut * vs, acc[8] += ut * ws;
+            acc[9] += vt * us, acc[10] += vt * vs, acc[11] += vt * ws;
+            acc[12] += wt * us, acc[13] += wt * vs, acc[14] += wt * ws;
+        } else if (cfg.variant == SE3ICP_PT2PL) {
+            const double nx = T.nrm[j], ny = T.nrm[m + j], nz = T.nrm[2 * m + j];
+            const double r = dx * nx + dy * ny + dz * nz;
+            double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+            int o = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+#pragma unroll
+                for (int b = a; b < 6; b++) acc[o++] += J[a] * J[b];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[21 + a] += J[a] * r;
+        } else {
+            // M = Ct + R Cs0 R^T ; B = M^-1 (times w^2) ; A = [-[s]x | I] ; JTJ += A^T B A ; JTr += A^T B d
+            double c0[6];
+#pragma unroll
+            for (int e = 0; e < 6; e++) c0[e] = S.cov[e * n + i];
+            double R[3][3] = {{Tm[0], Tm[1], Tm[2]}, {Tm[4], Tm[5], Tm[6]}, {Tm[8], Tm[9], Tm[10]}};
+            double C[3][3] = {{c0[0], c0[1], c0[2]}, {c0[1], c0[3], c0[4]}, {c0[2], c0[4], c0[5]}};
+            double RC[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) RC[r][c] = R[r][0] * C[0][c] + R[r][1] * C[1][c] + R[r][2] * C[2][c];
+            double Mm[6];
+            {
+                int e = 0;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = r; c < 3; c++) {
+                        double v = RC[r][0] * R[c][0] + RC[r][1] * R[c][1] + RC[r][2] * R[c][2];
+                        Mm[e] = v + T.cov[e * m + j];
+                        e++;
+                    }
+            }
+            double Bi[6];
+            sym3_inverse(Mm, Bi);
+            double w2 = 1.0;
+            if (cfg.with_cf) {
+                double w = (S.conf[i] + T.conf[j]) / 2.0;  // .cpp:913
+                w2 = w * w;
+            }
+            double B[3][3] = {{Bi[0] * w2, Bi[1] * w2, Bi[2] * w2},
+                              {Bi[1] * w2, Bi[3] * w2, Bi[4] * w2},
+                              {Bi[2] * w2, Bi[4] * w2, Bi[5] * w2}};
+            // columns of A = [-[s]x | I]: a0 = e_x x s, a1 = e_y x s, a2 = e_z x s, a3..5 = e_x, e_y, e_z
+            double A[6][3] = {{0.0, -sz, sy}, {sz, 0.0, -sx}, {-sy, sx, 0.0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            double BA[6][3];
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) BA[a][r] = B[r][0] * A[a][0] + B[r][1] * A[a][1] + B[r][2] * A[a][2];
+            int o = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+#pragma unroll
+                for (int b = a; b < 6; b++) acc[o++] += A[a][0] * BA[b][0] + A[a][1] * BA[b][1] + A[a][2] * BA[b][2];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[21 + a] += BA[a][0] * dx + BA[a][1] * dy + BA[a][2] * dz;
+        }
+    }
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kAcc; k++) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) sm[w][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double s = 0.0;
+        for (int k = 0; k < 8; k++) s += sm[k][threadIdx.x];
+        partials[blockIdx.x * kReducePartials + threadIdx.x] = s;
+    }
+}
+
+int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                  double* partials, cudaStream_t st) {
+    reduce_kernel<<<kReduceBlocks, 256, 0, st>>>(S, T, cfg, state, cb, partials);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve + update (one warp)
+// ------------------------------------------------------------------------------------------------
+// pivoted LDL^T of a symmetric 6x6 (diagonal pivoting, like Eigen::LDLT which Open3D's
+// SolveLinearSystemPSD calls); returns false when the solution is not finite
+__device__ bool ldlt6_solve(const double Ain[6][6], const double bin[6], double x[6]) {
+    double A[6][6], L[6][6], D[6], b[6];
+    int perm[6];
+    for (int i = 0; i < 6; i++) {
+        perm[i] = i;
+        b[i] = bin[i];
+        for (int j = 0; j < 6; j++) {
+            A[i][j] = Ain[i][j];
+            L[i][j] = 0.0;
+        }
+    }
+    for (int k = 0; k < 6; k++) {
+        int piv = k;
+        double big = fabs(A[k][k]);
+        for (int i = k + 1; i < 6; i++)
+            if (fabs(A[i][i]) > big) {
+                big = fabs(A[i][i]);
+                piv = i;
+            }
+        if (piv != k) {
+            for (int j = 0; j < 6; j++) { double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
+            for (int i = 0; i < 6; i++) { double t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
+            for (int j = 0; j < k; j++) { double t = L[k][j]; L[k][j] = L[piv][j]; L[piv][j] = t; }
+            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        D[k] = A[k][k];
+        L[k][k] = 1.0;
+        if (D[k] == 0.0) continue;
+        for (int i = k + 1; i < 6; i++) L[i][k] = A[i][k] / D[k];
+        for (int i = k + 1; i < 6; i++)
+            for (int j = k + 1; j < 6; j++) A[i][j] -= L[i][k] * D[k] * L[j][k];
+    }
+    double y[6], z[6];
+    for (int i = 0; i < 6; i++) y[i] = b[perm[i]];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < i; j++) y[i] -= L[i][j] * y[j];
+    for (int i = 0; i < 6; i++) z[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
+    for (int i = 5; i >= 0; i--)
+        for (int j = i + 1; j < 6; j++) z[i] -= L[j][i] * z[j];
+    bool ok = true;
+    for (int i = 0; i < 6; i++) {
+        x[perm[i]] = z[i];
+        ok = ok && isfinite(z[i]);
+    }
+    return ok;
+}
+
+// Open3D TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x3..5 (row-major out)
+__device__ void vector6_to_T(const double x[6], double Tm[16]) {
+    double cx = cos(x[0]), sx = sin(x[0]), cy = cos(x[1]), sy = sin(x[1]), cz = cos(x[2]), sz = sin(x[2]);
+    // Rz*Ry*Rx expanded
+    Tm[0] = cz * cy;  Tm[1] = cz * sy * sx - sz * cx;  Tm[2] = cz * sy * cx + sz * sx;  Tm[3] = x[3];
+    Tm[4] = sz * cy;  Tm[5] = sz * sy * sx + cz * cx;  Tm[6] = sz * sy * cx - cz * sx;  Tm[7] = x[4];
+    Tm[8] = -sy;      Tm[9] = cy * sx;                 Tm[10] = cy * cx;                Tm[11] = x[5];
+    Tm[12] = 0.0;     Tm[13] = 0.0;                    Tm[14] = 0.0;                    Tm[15] = 1.0;
+}
+
+__device__ double det3(const double A[3][3]) {
+    return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+}
+
+// Kabsch rotation from sigma = (1/K) sum (t - mu_t)(s - mu_s)^T  (Eigen::umeyama, no scaling)
+__device__ void kabsch_rotation(const double Sg[3][3], double R[3][3]) {
+    double a6[6];
+    {   // Sg^T Sg
+        double G[3][3];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) G[i][j] = Sg[0][i] * Sg[0][j] + Sg[1][i] * Sg[1][j] + Sg[2][i] * Sg[2][j];
+        a6[0] = G[0][0], a6[1] = G[0][1], a6[2] = G[0][2], a6[3] = G[1][1], a6[4] = G[1][2], a6[5] = G[2][2];
+    }
+    double ev[3], Va[3][3];
+    eig3_sym(a6, ev, Va);
+    double V[3][3], U[3][3], sv[3];
+    for (int c = 0; c < 3; c++) {  // descending singular values
+        int src = 2 - c;
+        sv[c] = sqrt(fmax(ev[src], 0.0));
+        for (int r = 0; r < 3; r++) V[r][c] = Va[r][src];
+    }
+    double u[3][3];  // u[c] = column c
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) u[c][r] = Sg[r][0] * V[0][c] + Sg[r][1] * V[1][c] + Sg[r][2] * V[2][c];
+    auto nrm = [](const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    auto dot3 = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    auto cross3 = [](const double* a, const double* b, double* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1];
+        o[1] = a[2] * b[0] - a[0] * b[2];
+        o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    double n0 = nrm(u[0]);
+    if (n0 > 0.0) { for (int r = 0; r < 3; r++) u[0][r] /= n0; } else { u[0][0] = 1; u[0][1] = 0; u[0][2] = 0; }
+    double tiny = 1e-14 * fmax(sv[0], 1e-300);
+    double d10 = dot3(u[1], u[0]);
+    for (int r = 0; r < 3; r++) u[1][r] -= d10 * u[0][r];
+    double n1 = nrm(u[1]);
+    if (n1 > tiny) {
+        for (int r = 0; r < 3; r++) u[1][r] /= n1;
+    } else {
+        double t[3] = {fabs(u[0][0]) < 0.9 ? 1.0 : 0.0, fabs(u[0][0]) < 0.9 ? 0.0 : 1.0, 0.0};
+        cross3(u[0], t, u[1]);
+        double nn = nrm(u[1]);
+        for (int r = 0; r < 3; r++) u[1][r] /= nn;
+    }
+    double d20 = dot3(u[2], u[0]);
+    for (int r = 0; r < 3; r++) u[2][r] -= d20 * u[0][r];
+    double d21 = dot3(u[2], u[1]);
+    for (int r = 0; r < 3; r++) u[2][r] -= d21 * u[1][r];
+    double n2 = nrm(u[2]);
+    if (n2 > tiny) {
+        for (int r = 0; r < 3; r++) u[2][r] /= n2;
+    } else {
+        cross3(u[0], u[1], u[2]);
+    }
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) U[r][c] = u[c][r];
+    double d = (det3(U) * det3(V) < 0.0) ? -1.0 : 1.0;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + d * U[r][2] * V[c][2];
+}
+
+__global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterState* __restrict__ st,
+                                                           const double* __restrict__ partials, double* __restrict__ history,
+                                                           unsigned int* __restrict__ hist) {
+    if (st->done) return;
+    __shared__ double tot[kReducePartials];
+    const int lane = threadIdx.x;
+    if (lane < kAcc) {
+        double s = 0.0;
+        for (int b = 0; b < kReduceBlocks; b++) s += partials[b * kReducePartials + lane];  // fixed order
+        tot[lane] = s;
+    }
+    if (hist)
+        for (int k = lane; k < 4 * 256; k += 32) hist[k] = 0;  // ready for the next iteration's trim
+    __syncwarp();
+    if (lane != 0) return;
+
+    const double K = tot[28];
+    const double mean = tot[27] / K;  // 0/0 -> NaN exactly as the reference
+    double Ti[16];
+    for (int k = 0; k < 16; k++) Ti[k] = (k % 5 == 0) ? 1.0 : 0.0;
+
+    if (K > 0.0) {
+        if (cfg.variant == SE3ICP_PT2PT) {
+            const double* Tm = st->T_total;
+            double c0[3] = {cfg.has_se3 ? 0.0 : st->c_src[0], cfg.has_se3 ? 0.0 : st->c_src[1],
+                            cfg.has_se3 ? 0.0 : st->c_src[2]};
+            double a[3], b[3] = {0, 0, 0};
+            for (int r = 0; r < 3; r++) a[r] = Tm[4 * r] * c0[0] + Tm[4 * r + 1] * c0[1] + Tm[4 * r + 2] * c0[2] + Tm[4 * r + 3];
+            if (!cfg.has_se3)
+                for (int r = 0; r < 3; r++) b[r] = st->c_tgt[r];
+            double ms[3] = {tot[0] / K, tot[1] / K, tot[2] / K};  // mu_s - a
+            double mt[3] = {tot[3] / K, tot[4] / K, tot[5] / K};  // mu_t - b
+            double Sg[3][3];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) Sg[r][c] = tot[6 + 3 * r + c] / K - mt[r] * ms[c];
+            double R[3][3];
+            kabsch_rotation(Sg, R);
+            double mus[3] = {ms[0] + a[0], ms[1] + a[1], ms[2] + a[2]};
+            double mut[3] = {mt[0] + b[0], mt[1] + b[1], mt[2] + b[2]};
+            for (int r = 0; r < 3; r++) {
+                for (int c = 0; c < 3; c++) Ti[4 * r + c] = R[r][c];
+                Ti[4 * r + 3] = mut[r] - (R[r][0] * mus[0] + R[r][1] * mus[1] + R[r][2] * mus[2]);
+            }
+        } else {
+            double A[6][6], rhs[6], x[6];
+            int o = 0;
+            for (int a = 0; a < 6; a++)
+                for (int b = a; b < 6; b++) {
+                    A[a][b] = tot[o];
+                    A[b][a] = tot[o];
+                    o++;
+                }
+            for (int a = 0; a < 6; a++) rhs[a] = -tot[21 + a];
+            if (ldlt6_solve(A, rhs, x)) vector6_to_T(x, Ti);
+        }
+    }
+
+    // bookkeeping: reference .cpp:684-686, 709-711
+    st->mse_prev = st->mse_cur;
+    st->mse_cur = mean;
+    st->mse_rel = fabs(st->mse_cur - st->mse_prev);
+    double Tn[16];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            double s = 0.0;
+            for (int k = 0; k < 4; k++) s += Ti[4 * r + k] * st->T_total[4 * k + c];
+            Tn[4 * r + c] = s;
+        }
+    double ch = 0.0;
+    for (int k = 0; k < 16; k++) {
+        double df = st->T_total[k] - Tn[k];
+        ch += df * df;
+        st->T_prev[k] = st->T_total[k];
+        st->T_i[k] = Ti[k];
+    }
+    for (int k = 0; k < 16; k++) st->T_total[k] = Tn[k];
+    st->T_change = sqrt(ch);
+    if (cfg.record_history && history && st->hist_count < cfg.max_history) {
+        for (int k = 0; k < 16; k++) history[16 * (size_t)st->hist_count + k] = Ti[k];
+        st->hist_count++;
+    }
+
+    const bool se3_now = se3_phase_active_o(cfg, st);
+    st->iter += 1;
+    if (se3_now) st->se3_iters += 1;
+    const double s = st->scale;
+    if (!cfg.has_se3) {  // run_icp .cpp:547-550
+        if (st->iter == cfg.max_iter || st->mse_rel < cfg.mse) st->done = 1;
+    } else if (cfg.pure) {  // run_se3_pure .cpp:1118
+        if (st->iter == cfg.max_se3_iter || st->mse_rel < s * cfg.mse) st->done = 1;
+    } else if (!st->switch_icp) {  // .cpp:718-723
+        if (st->iter == cfg.max_se3_iter || st->T_change < cfg.mse_switch) {
+            st->switch_icp = 1;
+            st->t_switch = global_timer_ns();
+        }
+    } else {  // .cpp:724-729
+        if (st->iter == cfg.max_iter || st->mse_rel < s * cfg.mse) st->done = 1;
+    }
+    st->total_repairs += st->repair_count;
+    st->repair_count = 0;
+    st->t_mark = global_timer_ns();
+}
+
+int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, double* history,
+                        unsigned int* hist, cudaStream_t st) {
+    solve_update_kernel<<<1, 32, 0, st>>>(cfg, state, partials, history, hist);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// reference .cpp:735-738: t = t'/s - R' c_src + c_tgt (rotation unchanged)
+__global__ void finalize_kernel(RunConfig cfg, IterState* st) {
+    if (threadIdx.x != 0) return;
+    for (int k = 0; k < 16; k++) st->T_final[k] = st->T_total[k];
+    if (cfg.has_se3) {
+        double inv = 1.0 / st->scale;
+        for (int r = 0; r < 3; r++) {
+            double rc = st->T_total[4 * r] * st->c_src[0] + st->T_total[4 * r + 1] * st->c_src[1] +
+                        st->T_total[4 * r + 2] * st->c_src[2];
+            st->T_final[4 * r + 3] = inv * st->T_total[4 * r + 3] - rc + st->c_tgt[r];
+        }
+    }
+}
+
+int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st) {
+    finalize_kernel<<<1, 32, 0, st>>>(cfg, state);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_init_state(IterState* state, unsigned int* hist, cudaStream_t st) {
+    init_state_kernel<<<1, 32, 0, st>>>(state, hist);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se3

@@ -1,0 +1,71 @@
+// traverse.cuh — warp-cooperative traversal of the implicit 32-wide box hierarchy.
+// One warp owns one query; each step a lane tests one child box, survivors are compacted onto a
+// per-warp stack in shared memory with their lower bound so they can be re-tested against the
+// shrinking search radius when popped.
+#pragma once
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace se3 {
+
+constexpr int kStackEntries = 192;  // >= 31 * levels + 1 for up to 6 levels (n <= 32^6)
+
+__device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node, double qx, double qy, double qz) {
+    const float* b = I.box + node;
+    size_t tn = (size_t)I.total_nodes;
+    double lox = b[0], loy = b[tn], loz = b[2 * tn];
+    double hix = b[3 * tn], hiy = b[4 * tn], hiz = b[5 * tn];
+    double dx = fmax(0.0, fmax(lox - qx, qx - hix));
+    double dy = fmax(0.0, fmax(loy - qy, qy - hiy));
+    double dz = fmax(0.0, fmax(loz - qz, qz - hiz));
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// `tau` is read on every test, so the leaf functor may shrink it while the traversal runs.
+// leaf_fn(leaf_id) is called by the whole warp (convergent).
+template <class LeafFn>
+__device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, double qy, double qz, const double& tau,
+                                               int2* stack, int lane, LeafFn&& leaf_fn) {
+    const double kSlack = 1.0 - 1e-12;  // never prune on a rounding-level difference
+    int sp = 0;
+    {
+        int top = I.n_levels - 1;
+        int cnt = I.level_cnt[top];
+        double lb = 0.0;
+        bool ok = false;
+        if (lane < cnt) {
+            lb = box_lower_bound(I, I.level_off[top] + lane, qx, qy, qz);
+            ok = lb * kSlack <= tau;
+        }
+        unsigned m = __ballot_sync(SE3_FULL, ok);
+        if (ok) stack[sp + __popc(m & ((1u << lane) - 1u))] = make_int2((top << 27) | lane, __float_as_int(__double2float_rd(lb)));
+        sp += __popc(m);
+        __syncwarp();
+    }
+    while (sp > 0) {
+        int2 e = stack[sp - 1];
+        sp--;
+        __syncwarp();
+        if ((double)__int_as_float(e.y) * kSlack > tau) continue;
+        int lvl = e.x >> 27, node = e.x & ((1 << 27) - 1);
+        if (lvl == 0) {
+            leaf_fn(node);
+            continue;
+        }
+        int cl = lvl - 1;
+        int c = node * 32 + lane;
+        double lb = 0.0;
+        bool ok = false;
+        if (c < I.level_cnt[cl]) {
+            lb = box_lower_bound(I, I.level_off[cl] + c, qx, qy, qz);
+            ok = lb * kSlack <= tau;
+        }
+        unsigned m = __ballot_sync(SE3_FULL, ok);
+        if (ok) stack[sp + __popc(m & ((1u << lane) - 1u))] = make_int2((cl << 27) | c, __float_as_int(__double2float_rd(lb)));
+        sp += __popc(m);
+        __syncwarp();
+    }
+}
+
+}  // namespace se3

@@ -1,0 +1,142 @@
+"""Python mirror of the reference class IterativeSE3Registration
+(reference include/iterative_SE3_registration.hpp:27-99, src/iterative_SE3_registration.cpp:334-1128).
+
+Same method names, public field names, defaults and error behaviour as the C++ class, so scripts and
+tests read like the reference's drivers (examples/run_registration_method.cpp:35-60).  All numeric
+work happens in libse3icp_cuda.so through the C ABI; nothing here computes on the CPU.
+"""
+import sys
+
+import numpy as np
+
+from . import capi
+
+
+class IterativeSE3Registration:
+    def __init__(self, device=0, stream=None):
+        # defaults: reference .cpp:334-348
+        self.max_num_iterations_ = 150
+        self.max_num_se3_iterations_ = 20
+        self.num_iterations_ = 0
+        self.num_pure_se3_iterations_ = -1
+        self.mse_ = 0.00001
+        self.lrf_radius_ = 0.8  # only used by the (dead) SHOT frame of the reference
+        self.mse_switch_error_ = 0.001
+        self.number_of_nn_for_LRF_ = 30
+        self.estimated_overlap_ = 1.0
+        self.alpha_rot = 3.0
+        self.beta_transl = 1.0
+        self.scale_preprocessing = 3.0
+        self.time_before_pure_icp_ = 0.0
+        self.time_se3_correspondence_search_ = 0.0
+        self.current_estimated_T_ = np.eye(4)
+        self.estimated_history_ = []
+        # extensions (not in the reference): comparator direction of the trimmed rejector and NN strategy
+        self.trim_keep_largest_ = False
+        self.nn_mode_ = capi.NN_AUTO
+        self._source = np.zeros((0, 3))
+        self._target = np.zeros((0, 3))
+        self._ctx = capi.Context(device, stream)
+        self.last_stats = None
+
+    # reference .cpp:358-366 / :372-376: the cloud overloads append
+    def setSourceCloud(self, cloud):
+        self._source = np.concatenate([self._source, np.asarray(cloud, dtype=np.float64).reshape(-1, 3)])
+
+    def setTargetCloud(self, cloud):
+        self._target = np.concatenate([self._target, np.asarray(cloud, dtype=np.float64).reshape(-1, 3)])
+
+    def _params(self, entry, variant):
+        return capi.default_params(
+            variant=variant, entry=entry, max_num_iterations=self.max_num_iterations_,
+            max_num_se3_iterations=self.max_num_se3_iterations_, number_of_nn_for_LRF=self.number_of_nn_for_LRF_,
+            trim_keep_largest=int(self.trim_keep_largest_), mse=self.mse_, mse_switch_error=self.mse_switch_error_,
+            estimated_overlap=self.estimated_overlap_, alpha_rot=self.alpha_rot, beta_transl=self.beta_transl,
+            scale_preprocessing=self.scale_preprocessing, nn_mode=self.nn_mode_, record_history=int(entry == capi.RUN_ICP))
+
+    def _run(self, entry, variant_name):
+        if variant_name not in capi.VARIANTS:
+            return self._invalid_variant(entry)
+        self._ctx.set_cloud(capi.SOURCE, self._source)
+        self._ctx.set_cloud(capi.TARGET, self._target)
+        T, st = self._ctx.run(self._params(entry, capi.VARIANTS[variant_name]))
+        self.current_estimated_T_ = T
+        self.num_iterations_ = st.num_iterations
+        if entry != capi.RUN_ICP:
+            self.num_pure_se3_iterations_ = st.num_pure_se3_iterations
+            self.time_se3_correspondence_search_ = st.time_se3_correspondence_search_ms if entry == capi.RUN_SE3_ICP_CF else 0.0
+        if entry == capi.RUN_SE3_ICP_CF:
+            self.time_before_pure_icp_ = st.time_before_pure_icp_ms
+        if entry == capi.RUN_ICP:  # .cpp:491,538
+            self.estimated_history_.append(np.eye(4))
+            self.estimated_history_.extend(list(self._ctx.history(max(self.max_num_iterations_, 1))))
+        self.last_stats = st
+        return T
+
+    def _invalid_variant(self, entry):
+        # reference: message on stderr; run_se3_icp/pure break at the first optimisation (.cpp:700-703) leaving
+        # R = I and, through .cpp:735-738, t = c_tgt - c_src; run_icp's behaviour is undefined -> identity here.
+        if entry == capi.RUN_ICP:
+            sys.stderr.write("Invalid ICP variant name. Valid names are pt2pt, pt2pl and gicp.\n")
+            self.current_estimated_T_ = np.eye(4)
+            return self.current_estimated_T_
+        sys.stderr.write("Invalid variant name. Choose one of: pt2pt, pt2pl, gicp \n")
+        T = np.eye(4)
+        T[:3, 3] = self._target.mean(axis=0) - self._source.mean(axis=0)
+        self.current_estimated_T_ = T
+        self.num_iterations_ = 1
+        self.num_pure_se3_iterations_ = 1
+        return T
+
+    def run_icp(self, variant_name):
+        return self._run(capi.RUN_ICP, variant_name)
+
+    def run_se3_icp(self, variant_name):
+        return self._run(capi.RUN_SE3_ICP, variant_name)
+
+    def run_se3_icp_with_cf(self):
+        return self._run(capi.RUN_SE3_ICP_CF, "gicp")
+
+    def run_se3_pure(self, variant_name):
+        return self._run(capi.RUN_SE3_PURE, variant_name)
+
+    # state the reference keeps as public members (hpp:59-60,74)
+    @property
+    def source_se3_cloud_(self):
+        return self._ctx.se3_cloud(capi.SOURCE)
+
+    @property
+    def target_se3_cloud_(self):
+        return self._ctx.se3_cloud(capi.TARGET)
+
+    @property
+    def current_correspondences_set(self):
+        return self._ctx.correspondences()
+
+
+METHODS = ("pt2pt", "pt2pl", "gicp", "se3_pt2pt", "se3_pt2pl", "se3_gicp", "se3_gicp_with_cf")
+
+
+def run_registration_method(method, source, target, **fields):
+    """examples/run_registration_method.cpp:35-57 as a function: method in METHODS; returns the object."""
+    reg = IterativeSE3Registration(device=fields.pop("device", 0))
+    reg.setSourceCloud(source)
+    reg.setTargetCloud(target)
+    reg.estimated_overlap_ = 1.0
+    reg.max_num_se3_iterations_ = 10
+    reg.mse_ = 0.00001
+    reg.mse_switch_error_ = 5 * reg.mse_
+    reg.number_of_nn_for_LRF_ = 90
+    for k, v in fields.items():
+        if not hasattr(reg, k):
+            raise AttributeError(k)
+        setattr(reg, k, v)
+    if method in ("pt2pt", "pt2pl", "gicp"):
+        reg.run_icp(method)
+    elif method in ("se3_pt2pt", "se3_pt2pl", "se3_gicp"):
+        reg.run_se3_icp(method[4:])
+    elif method == "se3_gicp_with_cf":
+        reg.run_se3_icp_with_cf()
+    else:
+        raise ValueError("Not a valid algorithm name; available: %s" % ", ".join(METHODS))
+    return reg

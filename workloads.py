@@ -1,0 +1,217 @@
+"""Synthetic workloads for tests and bench.py (the reference's gdrive datasets are not available offline).
+
+Shapes follow BASELINE.json `configs` / SURVEY.md §8(d):
+  C1  bundled fixture (tests/golden/c1_*.npy)
+  C2  stanford bunny x50 with Gaussian noise and easy/moderate/difficult ground truth
+      (reference examples/benchmark_synthetic.cpp:13-56,91-116)
+  C3  KITTI-like spinning-LiDAR scan pairs, ~120 k points (reference examples/benchmark_kitti.cpp:120-148)
+  C4  lounge-like RGB-D frame pairs, ~300 k points (reference examples/benchmark_lounge.cpp:154-186)
+Nothing here is product code.
+"""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rot_3d(roll, pitch, yaw):
+    """reference src/cc.cpp:22-30: q = yaw(Z) * pitch(Y) * roll(X)."""
+    cx, sx, cy, sy, cz, sz = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def make_T(R, t):
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = t
+    return T
+
+
+def apply_T(T, pts):
+    return pts @ T[:3, :3].T + T[:3, 3]
+
+
+def rotation_error(A, B):
+    """reference src/cc.cpp:49-61 angularErrorSO3_alt, in radians."""
+    c = (np.trace(A[:3, :3].T @ B[:3, :3]) - 1.0) / 2.0
+    return float(np.arccos(np.clip(c, -1.0, 1.0)))
+
+
+def load_c1():
+    return (np.load(os.path.join(GOLDEN, "c1_source.npy")), np.load(os.path.join(GOLDEN, "c1_target.npy")),
+            np.load(os.path.join(GOLDEN, "c1_T_gt.npy")))
+
+
+def load_bunny(scale=50.0):
+    """unique vertices of stanford_bunny.ply (34 834), scaled by 50 as benchmark_synthetic.cpp:95."""
+    return np.load(os.path.join(GOLDEN, "bunny_unique_f32.npy")).astype(np.float64) * scale
+
+
+LEVELS = {"easy": (np.pi / 4, 5.0), "moderate": (np.pi / 2, 10.0), "difficult": (np.pi, 15.0)}
+
+
+def bunny_problem(level="easy", seed=1, n_points=None, noise=0.005):
+    """benchmark_synthetic.cpp:104-116,150-160: GT angles U(+-a), translation U(+-t); independent
+    N(0, noise*I) on source and target.  n_points: random down-sample (the reference uses 2 %)."""
+    rng = np.random.default_rng(seed)
+    pts = load_bunny()
+    if n_points is not None and n_points < len(pts):
+        pts = pts[np.sort(rng.choice(len(pts), n_points, replace=False))]
+    a, t = LEVELS[level]
+    T = make_T(rot_3d(*rng.uniform(-a, a, 3)), rng.uniform(-t, t, 3))
+    sd = np.sqrt(noise)
+    src = pts + (rng.normal(0, sd, pts.shape) if noise > 0 else 0)
+    tgt = apply_T(T, pts) + (rng.normal(0, sd, pts.shape) if noise > 0 else 0)
+    return src, tgt, T
+
+
+# --------------------------------------------------------------------------------------------------
+# KITTI-like spinning LiDAR
+# --------------------------------------------------------------------------------------------------
+def _street_scene(rng):
+    """ground plane + boxes (buildings, cars) + vertical cylinders (poles, trunks) along a street."""
+    boxes = []
+    for side in (-1.0, 1.0):
+        x = -60.0
+        while x < 90.0:
+            w, d, h = rng.uniform(6, 18), rng.uniform(6, 14), rng.uniform(4, 14)
+            off = side * rng.uniform(9, 16)
+            y0, y1 = (off, off + side * d) if side > 0 else (off + side * d, off)
+            boxes.append((x, min(y0, y1), -1.73, x + w, max(y0, y1), -1.73 + h))
+            x += w + rng.uniform(1, 8)
+    for _ in range(14):  # parked cars
+        cx, side = rng.uniform(-50, 80), rng.choice([-1.0, 1.0])
+        cy = side * rng.uniform(3.5, 6.5)
+        boxes.append((cx, cy - 0.9, -1.73, cx + rng.uniform(3.8, 4.8), cy + 0.9, -1.73 + rng.uniform(1.3, 1.9)))
+    cyl = []
+    for _ in range(30):
+        cyl.append((rng.uniform(-55, 85), rng.choice([-1.0, 1.0]) * rng.uniform(6.5, 8.5), rng.uniform(0.08, 0.35),
+                    -1.73 + rng.uniform(3, 8)))
+    return np.array(boxes), np.array(cyl)
+
+
+def _ray_cast(origin, dirs, boxes, cyl, max_range):
+    """nearest hit distance for rays origin + s*dirs (world frame); inf where nothing within max_range."""
+    n = dirs.shape[0]
+    best = np.full(n, np.inf)
+    # ground z = -1.73
+    dz = dirs[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = (-1.73 - origin[2]) / dz
+    ok = (dz < 0) & (s > 0)
+    best = np.where(ok, np.minimum(best, s), best)
+    # axis-aligned boxes, slab method
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / dirs
+    for b in boxes:
+        t0 = (b[:3] - origin) * inv
+        t1 = (b[3:] - origin) * inv
+        tmin = np.nanmax(np.minimum(t0, t1), axis=1)
+        tmax = np.nanmin(np.maximum(t0, t1), axis=1)
+        hit = (tmax >= tmin) & (tmax > 0)
+        s = np.where(tmin > 0, tmin, tmax)
+        best = np.where(hit & (s < best), s, best)
+    # vertical cylinders (x0, y0, r, ztop), from the ground up
+    dxy = dirs[:, :2]
+    a = (dxy ** 2).sum(1)
+    for c in cyl:
+        oc = origin[:2] - c[:2]
+        bq = 2 * (dxy @ oc)
+        cq = oc @ oc - c[2] ** 2
+        disc = bq * bq - 4 * a * cq
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = (-bq - np.sqrt(np.maximum(disc, 0))) / (2 * a)
+        z = origin[2] + s * dirs[:, 2]
+        hit = (disc > 0) & (s > 0) & (z < c[3]) & (z > -1.73)
+        best = np.where(hit & (s < best), s, best)
+    best[best > max_range] = np.inf
+    return best
+
+
+def _lidar_scan(pose, boxes, cyl, rng, n_rings, n_az, max_range, sigma):
+    elev = np.deg2rad(np.linspace(-24.8, 2.0, n_rings))
+    az = np.linspace(0, 2 * np.pi, n_az, endpoint=False) + rng.uniform(0, 2 * np.pi / n_az)
+    ce, se_ = np.cos(elev)[:, None], np.sin(elev)[:, None]
+    d_s = np.stack([ce * np.cos(az)[None, :], ce * np.sin(az)[None, :], np.broadcast_to(se_, (n_rings, n_az))], -1)
+    d_s = d_s.reshape(-1, 3)
+    d_w = d_s @ pose[:3, :3].T
+    rng_hit = _ray_cast(pose[:3, 3], d_w, boxes, cyl, max_range)
+    ok = np.isfinite(rng_hit)
+    r = rng_hit[ok] + rng.normal(0, sigma, ok.sum())
+    return d_s[ok] * r[:, None]  # points in the sensor frame
+
+
+def lidar_pair(seed=0, n_rings=64, n_az=1900, max_range=80.0, sigma=0.02):
+    """Two consecutive scans of a static street scene.  Returns (source, target, T_gt) with
+    T_gt * source ~ target, i.e. scan i+1 registered onto scan i as benchmark_kitti.cpp:130-131."""
+    rng = np.random.default_rng(1000 + seed)
+    boxes, cyl = _street_scene(rng)
+    pose0 = make_T(rot_3d(0, 0, rng.uniform(-0.05, 0.05)), [rng.uniform(-5, 5), rng.uniform(-1, 1), 0.0])
+    step = make_T(rot_3d(rng.uniform(-0.005, 0.005), rng.uniform(-0.005, 0.005), np.deg2rad(rng.uniform(-3, 3))),
+                  [rng.uniform(1.0, 1.5), rng.uniform(-0.05, 0.05), rng.uniform(-0.02, 0.02)])
+    pose1 = pose0 @ step
+    tgt = _lidar_scan(pose0, boxes, cyl, rng, n_rings, n_az, max_range, sigma)
+    src = _lidar_scan(pose1, boxes, cyl, rng, n_rings, n_az, max_range, sigma)
+    return src, tgt, step  # p_0 = step * p_1
+
+
+KITTI_PARAMS = dict(estimated_overlap=0.7, mse=1e-7, mse_switch_error=5e-7, max_num_se3_iterations=10,
+                    number_of_nn_for_LRF=90, alpha_rot=3.0)  # benchmark_kitti.cpp:133-148
+
+
+# --------------------------------------------------------------------------------------------------
+# lounge-like RGB-D
+# --------------------------------------------------------------------------------------------------
+def rgbd_pair(seed=0, width=640, height=480, f=525.0, stride=1):
+    """Depth images of a box room with furniture boxes from two nearby camera poses (depth 0.4-4 m,
+    depth-dependent noise following the model in reference .cpp:25-27).  Returns (source, target, T_gt)."""
+    rng = np.random.default_rng(2000 + seed)
+    room = np.array([[-2.5, -1.4, -0.5, 2.5, 1.4, 3.7]])
+    boxes = []
+    for _ in range(10):
+        cx, cz = rng.uniform(-2.0, 2.0), rng.uniform(1.2, 3.2)
+        w, h, d = rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.2), rng.uniform(0.3, 0.9)
+        boxes.append((cx - w / 2, 1.4 - h, cz - d / 2, cx + w / 2, 1.4, cz + d / 2))  # standing on the floor (y down)
+    boxes = np.array(boxes)
+    u, v = np.meshgrid(np.arange(0, width, stride), np.arange(0, height, stride))
+    d_c = np.stack([(u - width / 2 + 0.5) / f, (v - height / 2 + 0.5) / f, np.ones_like(u, dtype=float)], -1).reshape(-1, 3)
+
+    def cast(pose):
+        o = pose[:3, 3]
+        d_w = d_c @ pose[:3, :3].T
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / d_w
+        # inside the room: exit distance of the room box
+        t0 = (room[0, :3] - o) * inv
+        t1 = (room[0, 3:] - o) * inv
+        best = np.nanmin(np.maximum(t0, t1), axis=1)
+        for b in boxes:
+            t0 = (b[:3] - o) * inv
+            t1 = (b[3:] - o) * inv
+            tmin = np.nanmax(np.minimum(t0, t1), axis=1)
+            tmax = np.nanmin(np.maximum(t0, t1), axis=1)
+            hit = (tmax >= tmin) & (tmin > 0)
+            best = np.where(hit & (tmin < best), tmin, best)
+        z = best  # d_c has unit z, so the ray parameter is the depth
+        sig = 0.002203 * z * z - 0.001028 * z + 0.0005351
+        z = z + rng.normal(0, 1, z.shape) * sig
+        ok = (z > 0.4) & (z < 4.0)
+        return d_c[ok] * z[ok, None]
+
+    pose0 = make_T(rot_3d(rng.uniform(-0.05, 0.05), rng.uniform(-0.2, 0.2), rng.uniform(-0.03, 0.03)),
+                   [rng.uniform(-0.5, 0.5), rng.uniform(-0.2, 0.2), rng.uniform(-0.3, 0.2)])
+    step = make_T(rot_3d(rng.uniform(-0.03, 0.03), rng.uniform(-0.08, 0.08), rng.uniform(-0.03, 0.03)),
+                  rng.uniform(-0.08, 0.08, 3))
+    pose1 = pose0 @ step
+    tgt = cast(pose0)
+    src = cast(pose1)
+    return src, tgt, step
+
+
+LOUNGE_PARAMS = dict(estimated_overlap=0.75, mse_switch_error=5e-5, max_num_se3_iterations=10,
+                     number_of_nn_for_LRF=90)  # benchmark_lounge.cpp:183-186
