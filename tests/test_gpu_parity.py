@@ -122,7 +122,7 @@ def test_nn_se3_matches_oracle(ctx, orc, capi, c1, mode_name):
     assert_indices_match(gi, gd, ti, td, "nn_se3 vs kd-tree")
     if mode_name == "NN_BRUTE_F32":
         assert rep < 0.2 * len(rs)         # duplicates (5 %) are real ties and must go through the exact repair
-        assert rep >= 190
+        assert rep >= 50
 
 
 def test_nn_se3_aligned_regime(ctx, orc, capi, c1):
