@@ -89,9 +89,14 @@ TargetView se3icp_ctx::target_view() const {
     T.nrm = nrm[1].as<double>();
     T.cov = cov[1].as<double>();
     T.conf = conf[1].as<double>();
-    T.rows32 = rows32.as<float4>();
-    T.rows64 = rows64.as<double>();
-    T.box12 = nullptr;
+    T.rows32 = se3idx.rows32.as<float4>();
+    T.rows64 = se3idx.rows64.as<double>();
+    T.box12 = se3idx.box12.as<float>();
+    T.perm12 = se3idx.perm12.as<int>();
+    T.inv12 = se3idx.inv12.as<int>();
+    T.keys12 = se3idx.keys12.as<uint64_t>();
+    T.tscale = cfg.with_cf ? 1.0 : cfg.beta;  // .cpp:834-836: the _with_cf tree holds the unscaled point
+    T.dist_scale = T.tscale != 0.0 ? cfg.beta / T.tscale : 0.0;
     return T;
 }
 
@@ -166,10 +171,7 @@ int alloc_run(se3icp_ctx* c) {
         SE3_TRY(c->psum[w].ensure((size_t)kReduceBlocks * 3 * sizeof(double)));
         SE3_TRY(c->pmax[w].ensure((size_t)kReduceBlocks * sizeof(double)));
     }
-    if (cfg.has_se3) {
-        SE3_TRY(c->rows32.ensure(3 * M * sizeof(float4)));
-        SE3_TRY(c->rows64.ensure(12 * M * sizeof(double)));
-    }
+    if (cfg.has_se3) SE3_TRY(c->se3idx.reserve((int)M, c->index[1].view));
     SE3_TRY(c->corr_idx.ensure(N * sizeof(int)));
     SE3_TRY(c->corr_dist.ensure(N * sizeof(double)));
     SE3_TRY(c->corr_distf.ensure(N * sizeof(float)));
@@ -240,11 +242,9 @@ int enqueue_setup(se3icp_ctx* c) {
         SE3_TRY(launch_knn_features(c->index[w].view, fa, st));
         c->launches += 1;
     }
-    if (cfg.has_se3) {
-        SE3_TRY(launch_pack_target_rows(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.beta, cfg.with_cf,
-                                        c->rows32.as<float4>(), c->rows64.as<double>(), ds, st));
-        c->launches += 1;
-    }
+    if (cfg.has_se3)  // .cpp:597-626: weighting, 12 x M matrix and its search structure
+        SE3_TRY(c->se3idx.build(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.with_cf ? 1.0 : cfg.beta, ds, st,
+                                &c->launches));
     SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, (size_t)N * sizeof(int), st));
     if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
     return 0;
@@ -258,10 +258,15 @@ int enqueue_iteration(se3icp_ctx* c) {
     CorrBuffers cb = c->corr_buffers(false);
     IterState* ds = c->dstate();
     if (cfg.has_se3) {
-        int force = c->params.nn_mode == SE3ICP_NN_EXACT_F64;
-        SE3_TRY(launch_nn_se3_brute(S, T, cfg, ds, cb, force, st));
-        SE3_TRY(launch_nn_se3_repair(S, T, cfg, ds, cb, st));
-        c->launches += 2;
+        int mode = c->params.nn_mode;
+        if (mode == SE3ICP_NN_BRUTE_F32 || mode == SE3ICP_NN_EXACT_F64) {
+            SE3_TRY(launch_nn_se3_brute(S, T, cfg, ds, cb, mode == SE3ICP_NN_EXACT_F64, st));
+            SE3_TRY(launch_nn_se3_repair(S, T, cfg, ds, cb, st));
+            c->launches += 2;
+        } else {  // AUTO / TREE: pruned traversal is the default (~10 of 3 730 leaves per query)
+            SE3_TRY(launch_nn_se3_tree(S, T, cfg, ds, cb, st));
+            c->launches += 1;
+        }
     }
     if (!cfg.pure) {
         SE3_TRY(launch_nn_xyz(S, T, cfg, ds, cb, st));
@@ -416,6 +421,10 @@ int se3icp_run_async(se3icp_ctx* c, const se3icp_params* p) {
     if (p->number_of_nn_for_LRF > SE3ICP_MAX_KNN || p->knn_normals_gicp > SE3ICP_MAX_KNN ||
         p->knn_normals_pt2pl > SE3ICP_MAX_KNN) {
         set_last_error("kNN sizes above %d are not supported", SE3ICP_MAX_KNN);
+        return SE3ICP_ERR_UNSUPPORTED;
+    }
+    if (p->nn_mode == SE3ICP_NN_TENSOR) {
+        set_last_error("SE3ICP_NN_TENSOR is not built (the pruned traversal made the brute-force sweep moot)");
         return SE3ICP_ERR_UNSUPPORTED;
     }
     SE3_TRY(fill_config(c, p));
@@ -624,7 +633,10 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
         SE3_CUDA(cudaEventRecord(e0, st));
         switch (stage) {
             case SE3ICP_STAGE_NN_SE3:
-                SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 0, st));
+                if (c->params.nn_mode == SE3ICP_NN_BRUTE_F32 || c->params.nn_mode == SE3ICP_NN_EXACT_F64)
+                    SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 0, st));
+                else
+                    SE3_TRY(launch_nn_se3_tree(S, T, cfg, c->dstate(), cb, st));
                 break;
             case SE3ICP_STAGE_NN_XYZ:
                 SE3_TRY(launch_nn_xyz(S, T, cfg, c->dstate(), cb, st));
@@ -834,11 +846,9 @@ int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double*
         for (int k = 0; k < 3; k++) xyz[3 * j + k] = tgt_rows[12 * j + 9 + k];
     SE3_TRY(upload_cloud_and_index(c, 1, xyz.data(), m));
     SE3_TRY(upload_planes(c, c->frame[1], tgt_rows, m, 9, 12, 0));
-    SE3_TRY(c->rows32.ensure(3 * m * sizeof(float4)));
-    SE3_TRY(c->rows64.ensure(12 * m * sizeof(double)));
     SE3_TRY(stage_state(c));
-    SE3_TRY(launch_pack_target_rows(c->index[1].view, c->frame[1].as<double>(), 1.0, 1.0, 0, c->rows32.as<float4>(),
-                                    c->rows64.as<double>(), c->dstate(), c->stream));
+    SE3_TRY(c->se3idx.reserve((int)m, c->index[1].view));
+    SE3_TRY(c->se3idx.build(c->index[1].view, c->frame[1].as<double>(), 1.0, 1.0, c->dstate(), c->stream, nullptr));
     // source
     SE3_TRY(upload_planes(c, c->frame[0], src_rows, n, 9, 12, 0));
     SE3_TRY(upload_planes(c, c->scratch, src_rows, n, 3, 12, 9));
@@ -849,24 +859,26 @@ int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double*
     S.y = S.x + n;
     S.z = S.x + 2 * n;
     S.frame = c->frame[0].as<double>();
-    TargetView T = c->target_view();
     RunConfig cfg;
     identity_config(cfg, SE3ICP_PT2PT, true);
+    c->cfg = cfg;  // target_view() reads beta / with_cf from the context's config
+    TargetView T = c->target_view();
     SE3_TRY(stage_corr_alloc(c, n));
     CorrBuffers cb = c->corr_buffers(true);
     switch (nn_mode) {
         case SE3ICP_NN_AUTO:
-        case SE3ICP_NN_BRUTE_F32:
-            SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 0, c->stream));
+        case SE3ICP_NN_TREE:
+            SE3_TRY(launch_nn_se3_tree(S, T, cfg, c->dstate(), cb, c->stream));
             break;
+        case SE3ICP_NN_BRUTE_F32:
         case SE3ICP_NN_EXACT_F64:
-            SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 1, c->stream));
+            SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, nn_mode == SE3ICP_NN_EXACT_F64, c->stream));
+            SE3_TRY(launch_nn_se3_repair(S, T, cfg, c->dstate(), cb, c->stream));
             break;
         default:
             set_last_error("nn_mode %d not available", nn_mode);
             return SE3ICP_ERR_UNSUPPORTED;
     }
-    SE3_TRY(launch_nn_se3_repair(S, T, cfg, c->dstate(), cb, c->stream));
     SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
     SE3_CUDA(cudaMemcpyAsync(idx, cb.idx, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (d2) SE3_CUDA(cudaMemcpyAsync(d2, cb.d2_nd, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -36,4 +36,13 @@ struct IndexStorage {
     int build(cudaStream_t st, long long* launches);
 };
 
+// 12-D search structure over the target's SE(3) rows (se3_index.cu)
+struct Se3IndexStorage {
+    DeviceBuf perm12, inv12, keys12, keys_tmp, vals_tmp, box12, rows32, rows64, sort_tmp;
+    size_t sort_tmp_bytes = 0;
+    int reserve(int n, const CloudIndex& levels);
+    int build(const CloudIndex& I, const double* frame, double alpha, double tscale, IterState* state, cudaStream_t st,
+              long long* launches);
+};
+
 }  // namespace se3

@@ -106,9 +106,15 @@ struct TargetView {
     const double* nrm;    // [3][n] or null
     const double* cov;    // [6][n] or null
     const double* conf;   // [n] or null
-    const float4* rows32; // [3][n] morton order
-    const double* rows64; // [12][n] morton order
-    const float* box12;   // [24][total_nodes] 12-D boxes for the pruned SE(3) search (or null)
+    // SE(3) search structure: rows in 6-D Morton order (se3_index.cu); level layout shared with idx
+    const float4* rows32; // [3][n]  (alpha R | tscale p) as floats
+    const double* rows64; // [12][n]
+    const float* box12;   // [24][total_nodes] lo[12], hi[12]
+    const int* perm12;    // 6-D position -> original index
+    const int* inv12;     // original index -> 6-D position
+    const uint64_t* keys12;
+    double tscale;        // scale of the translation part of the rows (beta; 1 for run_se3_icp_with_cf, .cpp:834-836)
+    double dist_scale;    // beta / tscale: stored distance uses beta * p (.cpp:465)
 };
 
 struct CorrBuffers {
@@ -149,8 +155,8 @@ int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t
 int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, double* cov /*[6][n]*/, cudaStream_t st);
 
 // nn_search.cu
-int launch_pack_target_rows(const CloudIndex& I, const double* frame, double alpha, double beta, int cf_unscaled_p,
-                            float4* rows32, double* rows64, IterState* state, cudaStream_t st);
+int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                       cudaStream_t st);
 int launch_nn_se3_brute(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,
                         CorrBuffers cb, int force_all_repair, cudaStream_t st);
 int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,

@@ -1,7 +1,8 @@
 // nn_search.cu — correspondence search.
 //
-//  * pack_target_rows   reference .cpp:597-626: alpha/beta weighting and the 12 x M data matrix, stored
-//                       in Morton order as float4 tiles (sweep) and FP64 planes (exact evaluation).
+//  * nn_se3_tree        reference .cpp:444-470 (update_correspondences_raw_flann_SE3): warp-per-query pruned
+//                       traversal of the 12-D box hierarchy built by se3_index.cu; FP32 directed-rounding
+//                       box bounds, exact FP64 leaf distances, warm-started from the previous match.
 //  * nn_se3_brute       reference .cpp:444-470 (update_correspondences_raw_flann_SE3): tiled FP32
 //                       sweep with top-2 tracking and a rigorous certification test; the query is
 //                       T_total * X0 formed on the fly (the reference's rewrite of source_se3_cloud_,
@@ -14,51 +15,13 @@
 #include "common.cuh"
 #include "internal.h"
 #include "morton.cuh"
+#include "se3_key.cuh"
 #include "traverse.cuh"
 
 namespace se3 {
 
 __device__ __forceinline__ bool se3_phase_active(const RunConfig& cfg, const IterState* st) {
     return cfg.has_se3 && (cfg.pure || !st->switch_icp);
-}
-
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_target_rows_kernel(CloudIndex I, const double* __restrict__ frame, double alpha,
-                                                                double beta, int cf_unscaled_p, float4* __restrict__ rows32,
-                                                                double* __restrict__ rows64, IterState* __restrict__ state) {
-    const size_t n = (size_t)I.n;
-    double amax = 0.0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < I.n; s += gridDim.x * blockDim.x) {
-        int o = I.perm[s];
-        double v[12];
-#pragma unroll
-        for (int k = 0; k < 9; k++) v[k] = frame[k * n + o] * alpha;  // .cpp:605
-        double px = I.sx[s], py = I.sy[s], pz = I.sz[s];
-        // .cpp:606 (beta) — run_se3_icp_with_cf feeds the tree the unscaled point (.cpp:834-836)
-        v[9] = cf_unscaled_p ? px : px * beta;
-        v[10] = cf_unscaled_p ? py : py * beta;
-        v[11] = cf_unscaled_p ? pz : pz * beta;
-#pragma unroll
-        for (int k = 0; k < 12; k++) {
-            rows64[k * n + s] = v[k];
-            amax = fmax(amax, fabs(v[k]));
-        }
-        rows32[s] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
-        rows32[n + s] = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
-        rows32[2 * n + s] = make_float4((float)v[8], (float)v[9], (float)v[10], (float)v[11]);
-    }
-    amax = warp_max(amax);
-    if ((threadIdx.x & 31) == 0 && amax > 0.0)
-        atomicMax(reinterpret_cast<unsigned long long*>(&state->tgt_absmax), (unsigned long long)__double_as_longlong(amax));
-}
-
-int launch_pack_target_rows(const CloudIndex& I, const double* frame, double alpha, double beta, int cf_unscaled_p,
-                            float4* rows32, double* rows64, IterState* state, cudaStream_t st) {
-    int g = (I.n + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
-    pack_target_rows_kernel<<<g, 256, 0, st>>>(I, frame, alpha, beta, cf_unscaled_p, rows32, rows64, state);
-    SE3_CUDA(cudaGetLastError());
-    return 0;
 }
 
 // query i: 12-vector of T_total * [alpha R0 | beta p0]  (reference .cpp:450-453 after .cpp:713-716)
@@ -94,11 +57,12 @@ __device__ __forceinline__ void write_se3_match(const TargetView& T, const RunCo
                                                 const double q[12], int j, double d2_12) {
     const size_t m = (size_t)T.n;
     // reference .cpp:465-467: stored distance is the 3-D distance of the translation columns
-    // (target_se3_cloud_ column = beta * p even in the _with_cf variant)
-    double tx = T.idx.sx[j] * cfg.beta, ty = T.idx.sy[j] * cfg.beta, tz = T.idx.sz[j] * cfg.beta;
-    (void)m;
+    // (target_se3_cloud_ column = beta * p even in the _with_cf variant, whose rows hold the unscaled p)
+    double tx = T.rows64[9 * m + j] * T.dist_scale, ty = T.rows64[10 * m + j] * T.dist_scale,
+           tz = T.rows64[11 * m + j] * T.dist_scale;
+    (void)cfg;
     double d3 = sqrt(sqdist3(q[9], q[10], q[11], tx, ty, tz));
-    cb.idx[i] = T.idx.perm[j];
+    cb.idx[i] = T.perm12[j];
     cb.dist[i] = d3;
     cb.distf[i] = (float)d3;
     if (cb.d2_nd) cb.d2_nd[i] = d2_12;
@@ -233,9 +197,9 @@ __global__ void __launch_bounds__(kRepairThreads) nn_se3_repair_kernel(SourceVie
             if (d2 < best) {
                 best = d2;
                 best_j = j;
-                best_id = T.idx.perm[j];
+                best_id = T.perm12[j];
             } else if (d2 == best) {
-                int id = T.idx.perm[j];
+                int id = T.perm12[j];
                 if (id < best_id) {
                     best_id = id;
                     best_j = j;
@@ -279,6 +243,102 @@ int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConf
                          cudaStream_t st) {
     int g = S.n < 148 * 4 ? (S.n > 0 ? S.n : 1) : 148 * 4;
     nn_se3_repair_kernel<<<g, kRepairThreads, 0, st>>>(S, T, cfg, state, cb);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kTreeWarps = 8;
+
+__global__ void __launch_bounds__(kTreeWarps * 32) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                                       IterState* __restrict__ state, CorrBuffers cb) {
+    if (state->done || !se3_phase_active(cfg, state)) return;
+    __shared__ int2 stacks[kTreeWarps][kStackEntries];
+    __shared__ double Tm[16];
+    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * kTreeWarps + wib;
+    if (i >= S.n) return;
+    const int M = T.n;
+    const size_t m = (size_t)M, tn = (size_t)T.idx.total_nodes;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    double q[12];
+    make_query(S, cfg, Tm, i, q);
+    float qlo[12], qhi[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        qlo[k] = __double2float_rd(q[k]);
+        qhi[k] = __double2float_ru(q[k]);
+    }
+    // rigorous FP32 lower bound: every operation rounds toward the smaller result
+    auto lb_fn = [&](int node) -> double {
+        const float* b = T.box12 + node;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            float lo = b[(size_t)k * tn], hi = b[(size_t)(12 + k) * tn];
+            float d = fmaxf(0.f, fmaxf(__fsub_rd(lo, qhi[k]), __fsub_rd(qlo[k], hi)));
+            acc = __fadd_rd(acc, __fmul_rd(d, d));
+        }
+        return (double)acc;
+    };
+
+    double tau = inf;
+    int best_id = 0x7fffffff, best_j = 0;
+    auto leaf_fn = [&](int leaf) {
+        int p = leaf * 32 + lane;
+        double d2 = inf;
+        int id = 0x7fffffff;
+        if (p < M) {
+            d2 = exact_d2_12(q, T.rows64, m, p);
+            id = T.perm12[p];
+        }
+        double wd = d2;
+        int wid = id;
+        warp_argmin(wd, wid);
+        if (wd < tau || (wd == tau && wid < best_id)) {
+            unsigned who = __ballot_sync(SE3_FULL, id == wid && d2 == wd);
+            tau = wd;
+            best_id = wid;
+            best_j = leaf * 32 + (__ffs(who) - 1);
+        }
+    };
+
+    int prev = cb.idx[i];
+    if (prev >= 0 && prev < M) {
+        best_j = T.inv12[prev];
+        best_id = prev;
+        tau = exact_d2_12(q, T.rows64, m, best_j);
+    } else {
+        // no warm start: the leaf around the query's own 6-D key gives the first radius
+        double Ru[9];
+        double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
+        double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
+        uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
+        int lo = 0, hi = M;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= M) lo = M - 1;
+        leaf_fn(lo >> 5);
+    }
+    traverse_nodes(T.idx, lb_fn, tau, stacks[wib], lane, leaf_fn);
+    if (lane == 0) write_se3_match(T, cfg, cb, i, q, best_j, tau);
+}
+
+int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                       cudaStream_t st) {
+    if (T.idx.n_levels > 6) {
+        set_last_error("cloud too large for the traversal stack");
+        return SE3ICP_ERR_UNSUPPORTED;
+    }
+    int g = (S.n + kTreeWarps - 1) / kTreeWarps;
+    nn_se3_tree_kernel<<<g, kTreeWarps * 32, 0, st>>>(S, T, cfg, state, cb);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }

@@ -23,10 +23,11 @@ __device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node,
 }
 
 // `tau` is read on every test, so the leaf functor may shrink it while the traversal runs.
-// leaf_fn(leaf_id) is called by the whole warp (convergent).
-template <class LeafFn>
-__device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, double qy, double qz, const double& tau,
-                                               int2* stack, int lane, LeafFn&& leaf_fn) {
+// lb_fn(node) returns a lower bound of the squared distance from the query to anything below the
+// node; leaf_fn(leaf_id) is called by the whole warp (convergent).
+template <class LbFn, class LeafFn>
+__device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn, const double& tau, int2* stack, int lane,
+                                               LeafFn&& leaf_fn) {
     const double kSlack = 1.0 - 1e-12;  // never prune on a rounding-level difference
     int sp = 0;
     {
@@ -35,7 +36,7 @@ __device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, d
         double lb = 0.0;
         bool ok = false;
         if (lane < cnt) {
-            lb = box_lower_bound(I, I.level_off[top] + lane, qx, qy, qz);
+            lb = lb_fn(I.level_off[top] + lane);
             ok = lb * kSlack <= tau;
         }
         unsigned m = __ballot_sync(SE3_FULL, ok);
@@ -58,7 +59,7 @@ __device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, d
         double lb = 0.0;
         bool ok = false;
         if (c < I.level_cnt[cl]) {
-            lb = box_lower_bound(I, I.level_off[cl] + c, qx, qy, qz);
+            lb = lb_fn(I.level_off[cl] + c);
             ok = lb * kSlack <= tau;
         }
         unsigned m = __ballot_sync(SE3_FULL, ok);
@@ -66,6 +67,12 @@ __device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, d
         sp += __popc(m);
         __syncwarp();
     }
+}
+
+template <class LeafFn>
+__device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, double qy, double qz, const double& tau,
+                                               int2* stack, int lane, LeafFn&& leaf_fn) {
+    traverse_nodes(I, [&](int node) { return box_lower_bound(I, node, qx, qy, qz); }, tau, stack, lane, leaf_fn);
 }
 
 }  // namespace se3

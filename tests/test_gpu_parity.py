@@ -111,7 +111,7 @@ def se3_rows_pair(orc, c1, T_apply=None):
     return rs, rt
 
 
-@pytest.mark.parametrize("mode_name", ["NN_BRUTE_F32", "NN_EXACT_F64"])
+@pytest.mark.parametrize("mode_name", ["NN_TREE", "NN_BRUTE_F32", "NN_EXACT_F64"])
 def test_nn_se3_matches_oracle(ctx, orc, capi, c1, mode_name):
     rs, rt = se3_rows_pair(orc, c1)
     gi, gd, rep = ctx.nn_se3(rs, rt, getattr(capi, mode_name))
@@ -136,10 +136,11 @@ def test_nn_se3_aligned_regime(ctx, orc, capi, c1):
     Tn[:3, 3] = [1e-3, -2e-3, 5e-4]
     rs = orc.se3_rows(np.einsum("ij,njk->nik", Tn, fs), 3.0, 1.0)
     rt = orc.se3_rows(ft, 3.0, 1.0)
-    gi, gd, rep = ctx.nn_se3(rs, rt, capi.NN_BRUTE_F32)
     oi, od = orc.nn(rs, rt, brute=True)
-    np.testing.assert_array_equal(gi, oi)
-    np.testing.assert_array_equal(gd, od)
+    for mode in (capi.NN_TREE, capi.NN_BRUTE_F32):
+        gi, gd, rep = ctx.nn_se3(rs, rt, mode)
+        np.testing.assert_array_equal(gi, oi)
+        np.testing.assert_array_equal(gd, od)
 
 
 def test_nn_se3_random_and_ragged(ctx, orc, capi):
@@ -148,7 +149,7 @@ def test_nn_se3_random_and_ragged(ctx, orc, capi):
         rs, rt = rng.normal(size=(n, 12)) * 2, rng.normal(size=(m, 12)) * 2
         if m > 2:
             rt[2] = rt[0]
-        for mode in (capi.NN_BRUTE_F32, capi.NN_EXACT_F64):
+        for mode in (capi.NN_TREE, capi.NN_BRUTE_F32, capi.NN_EXACT_F64):
             gi, gd, _ = ctx.nn_se3(rs, rt, mode)
             oi, od = orc.nn(rs, rt, brute=True)
             np.testing.assert_array_equal(gi, oi)
@@ -298,19 +299,21 @@ def test_registration_trimmed(ctx, orc, capi, overlap, keep_largest):
     assert sg.num_iterations == so.num_iterations
 
 
-def test_registration_exact_mode_equals_default(ctx, capi, c1):
-    """the FP32 sweep + certification + repair path returns what the all-FP64 path returns"""
-    src, tgt, _ = c1
+@pytest.mark.parametrize("problem", ["c1", "bunny"])
+def test_registration_nn_modes_agree(ctx, capi, c1, bunny4k, problem):
+    """pruned traversal, FP32 sweep + certified repair and the all-FP64 sweep give identical registrations"""
+    src, tgt, _ = c1 if problem == "c1" else bunny4k
     ctx.set_cloud(capi.SOURCE, src)
     ctx.set_cloud(capi.TARGET, tgt)
-    Ta, sa = ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM))
-    idx_a, dist_a = ctx.correspondences()
-    Tb, sb = ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, nn_mode=capi.NN_EXACT_F64, **RRM))
-    idx_b, dist_b = ctx.correspondences()
-    np.testing.assert_array_equal(Ta, Tb)
-    np.testing.assert_array_equal(idx_a, idx_b)
-    assert sa.num_iterations == sb.num_iterations
-    assert sa.exact_repairs < sb.exact_repairs
+    res = {}
+    for name in ("NN_TREE", "NN_BRUTE_F32", "NN_EXACT_F64"):
+        T, st = ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, nn_mode=getattr(capi, name), **RRM))
+        res[name] = (T, st, ctx.correspondences())
+    for name in ("NN_BRUTE_F32", "NN_EXACT_F64"):
+        np.testing.assert_array_equal(res["NN_TREE"][0], res[name][0])
+        np.testing.assert_array_equal(res["NN_TREE"][2][0], res[name][2][0])
+        assert res["NN_TREE"][1].num_iterations == res[name][1].num_iterations
+    assert res["NN_BRUTE_F32"][1].exact_repairs < res["NN_EXACT_F64"][1].exact_repairs
 
 
 def test_history_and_mirrors(pkg, capi, c1):
