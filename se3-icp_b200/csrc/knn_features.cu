@@ -13,88 +13,144 @@
 
 namespace se3 {
 
-constexpr int kCap = 256;  // candidate buffer entries per warp
 constexpr int kKnnWarps = 8;
+constexpr int kPend = 64;  // pending-candidate buffer per warp (merged into the list 32 at a time)
 
 struct KnnScratch {
-    double d[kCap];
-    int id[kCap];
+    unsigned long long d[kPend];
+    int id[kPend];
     int2 stack[kStackEntries];
 };
 
-// ascending bitonic sort of (d, id) pairs, P a power of two <= kCap, executed by one warp
-__device__ __forceinline__ void warp_sort_pairs(double* d, int* id, int P, int lane) {
-    for (int k = 2; k <= P; k <<= 1) {
+// The k-nearest list lives in registers: 128 (key, id) slots striped over the warp, element e in lane
+// e % 32, slot e / 32, ascending by (distance bits, original index).  Squared distances are >= 0, so
+// their IEEE bit patterns order like the values and integer compares replace FP64 compares.
+typedef unsigned long long key_t;
+constexpr key_t kInfKey = 0x7ff0000000000000ULL;
+
+__device__ __forceinline__ bool key_less(key_t da, int ia, key_t db, int ib) { return da < db || (da == db && ia < ib); }
+
+__device__ __forceinline__ void ce_lane(key_t& dl, int& il, key_t& dh, int& ih) {  // in-lane: low slot gets the min
+    if (key_less(dh, ih, dl, il)) {
+        key_t t = dl; dl = dh; dh = t;
+        int u = il; il = ih; ih = u;
+    }
+}
+
+__device__ __forceinline__ void ce_shfl(key_t& d, int& i, int j, bool keep_min) {  // with lane ^ j
+    key_t od = __shfl_xor_sync(SE3_FULL, d, j);
+    int oi = __shfl_xor_sync(SE3_FULL, i, j);
+    bool other_less = key_less(od, oi, d, i);
+    if (other_less == keep_min) {
+        d = od;
+        i = oi;
+    }
+}
+
+// sorts one (key, id) per lane ascending by lane
+__device__ __forceinline__ void warp_sort32(key_t& d, int& i, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (P >> 1); t += 32) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int p = i | j;
-                bool up = (i & k) == 0;
-                double di = d[i], dp = d[p];
-                int ii = id[i], ip = id[p];
-                bool gt = di > dp || (di == dp && ii > ip);
-                if (gt == up) {
-                    d[i] = dp;
-                    d[p] = di;
-                    id[i] = ip;
-                    id[p] = ii;
-                }
-            }
-            __syncwarp();
+            bool up = (lane & k) == 0;
+            bool lower = (lane & j) == 0;
+            ce_shfl(d, i, j, lower == up);
         }
     }
+}
+
+// merges 32 candidates (one per lane, any order; unused lanes hold kInfKey) into the sorted 128-list
+__device__ __forceinline__ void merge32(key_t (&Ld)[4], int (&Li)[4], key_t cd, int ci, int lane) {
+    warp_sort32(cd, ci, lane);
+    // element-wise min of the list tail (ascending) with the reversed batch (descending) -> bitonic 128
+    key_t bd = __shfl_sync(SE3_FULL, cd, 31 - lane);
+    int bi = __shfl_sync(SE3_FULL, ci, 31 - lane);
+    if (key_less(bd, bi, Ld[3], Li[3])) {
+        Ld[3] = bd;
+        Li[3] = bi;
+    }
+    ce_lane(Ld[0], Li[0], Ld[2], Li[2]);  // distance 64
+    ce_lane(Ld[1], Li[1], Ld[3], Li[3]);
+    ce_lane(Ld[0], Li[0], Ld[1], Li[1]);  // distance 32
+    ce_lane(Ld[2], Li[2], Ld[3], Li[3]);
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) ce_shfl(Ld[t], Li[t], j, lower);
+    }
+}
+
+// element e of the striped list, broadcast to every lane
+__device__ __forceinline__ void list_at(const key_t (&Ld)[4], const int (&Li)[4], int e, key_t& d, int& i) {
+    int slot = e >> 5;
+    key_t sd = slot == 0 ? Ld[0] : slot == 1 ? Ld[1] : slot == 2 ? Ld[2] : Ld[3];
+    int si = slot == 0 ? Li[0] : slot == 1 ? Li[1] : slot == 2 ? Li[2] : Li[3];
+    d = __shfl_sync(SE3_FULL, sd, e & 31);
+    i = __shfl_sync(SE3_FULL, si, e & 31);
 }
 
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex I, FeatureArgs fa) {
     __shared__ KnnScratch scratch[kKnnWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int s = blockIdx.x * kKnnWarps + wib;  // query = Morton position s
-    if (s >= I.n) return;
+    // query = Morton position s.  Warps past the end redo the last query without writing, so the whole
+    // block reaches the __syncthreads() of the batched eigen-solves below.
+    const int s_raw = blockIdx.x * kKnnWarps + wib;
+    const bool active = s_raw < I.n;
+    const int s = active ? s_raw : I.n - 1;
     KnnScratch& W = scratch[wib];
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
     const double qx = I.sx[s], qy = I.sy[s], qz = I.sz[s];
     const int self = I.perm[s];
     const int K = fa.K < I.n ? fa.K : I.n;
-    int cnt = 0;
-    double tau = inf;
+    key_t Ld[4] = {kInfKey, kInfKey, kInfKey, kInfKey};
+    int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    int pend = 0;           // candidates waiting in W.d / W.id
+    key_t tau_bits = kInfKey;
     int tau_id = 0x7fffffff;
+    double tau = __longlong_as_double((long long)kInfKey);
     const int n_leaves = I.level_cnt[0];
 
-    auto eval_leaf = [&](int leaf, bool filter) {
+    auto refresh_tau = [&]() {
+        list_at(Ld, Li, K - 1, tau_bits, tau_id);
+        tau = __longlong_as_double((long long)tau_bits);
+    };
+    // merge 32 pending candidates (the last 32 of the buffer) into the list
+    auto flush32 = [&]() {
+        int take = pend < 32 ? pend : 32;
+        int src = pend - take + lane;
+        key_t cd = kInfKey;
+        int ci = 0x7fffffff;
+        if (lane < take) {
+            cd = W.d[src];
+            ci = W.id[src];
+        }
+        __syncwarp();
+        pend -= take;
+        merge32(Ld, Li, cd, ci, lane);
+        refresh_tau();
+    };
+    auto eval_leaf = [&](int leaf) {
         int p = leaf * 32 + lane;
         bool pass = false;
-        double d2 = 0.0;
-        int id = 0;
+        key_t db = kInfKey;
+        int id = 0x7fffffff;
         if (p < I.n) {
-            d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
+            db = (key_t)__double_as_longlong(sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]));
             id = I.perm[p];
-            pass = !filter || d2 < tau || (d2 == tau && id < tau_id);
+            pass = key_less(db, id, tau_bits, tau_id);
         }
         unsigned m = __ballot_sync(SE3_FULL, pass);
+        if (m == 0u) return;
         if (pass) {
-            int pos = cnt + __popc(m & ((1u << lane) - 1u));
-            W.d[pos] = d2;
+            int pos = pend + __popc(m & ((1u << lane) - 1u));
+            W.d[pos] = db;
             W.id[pos] = id;
         }
-        cnt += __popc(m);
+        pend += __popc(m);
         __syncwarp();
-    };
-    auto compact = [&]() {
-        int P = 32;
-        while (P < cnt) P <<= 1;
-        for (int t = cnt + lane; t < P; t += 32) {
-            W.d[t] = inf;
-            W.id[t] = 0x7fffffff;
-        }
-        __syncwarp();
-        warp_sort_pairs(W.d, W.id, P, lane);
-        if (cnt > K) cnt = K;
-        if (cnt == K) {
-            tau = W.d[K - 1];
-            tau_id = W.id[K - 1];
-        }
-        __syncwarp();
+        if (pend >= 32) flush32();
     };
 
     // seed: the leaves around the query in Morton order give a near-final search radius
@@ -102,20 +158,24 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     const int half = (K + 63) / 64;
     const int w0 = L - half > 0 ? L - half : 0;
     const int w1 = L + half < n_leaves - 1 ? L + half : n_leaves - 1;
-    for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf, false);
-    compact();
+    for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
+    while (pend > 0) flush32();
 
     traverse_boxes(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
         if (leaf >= w0 && leaf <= w1) return;
-        eval_leaf(leaf, true);
-        if (cnt > kCap - 32) compact();
+        eval_leaf(leaf);
     });
-    compact();  // final: ascending, cnt = min(K, n)
+    while (pend > 0) flush32();
+    const int cnt = K;  // the list now holds the min(K, n) nearest, ascending, then padding
 
-    if (fa.knn_idx) {
-        for (int j = lane; j < fa.K; j += 32) {
-            fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? W.id[j] : -1;
-            if (fa.knn_d2) fa.knn_d2[(size_t)self * fa.K + j] = j < cnt ? W.d[j] : -1.0;
+    if (fa.knn_idx && active) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int j = lane + 32 * t;
+            if (j < fa.K) {
+                fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? Li[t] : -1;
+                if (fa.knn_d2) fa.knn_d2[(size_t)self * fa.K + j] = j < cnt ? __longlong_as_double((long long)Ld[t]) : -1.0;
+            }
         }
     }
     if (fa.k_lrf <= 0 && fa.k_nrm <= 0) return;
@@ -127,7 +187,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
         int j = lane + 32 * t;
         nx[t] = ny[t] = nz[t] = 0.0;
         if (j < cnt) {
-            int id = W.id[j];
+            int id = Li[t];
             nx[t] = I.x[id];
             ny[t] = I.y[id];
             nz[t] = I.z[id];
@@ -135,10 +195,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     }
     const size_t n = (size_t)I.n;
 
+    // ---- phase A: per-warp second moments; the 3x3 eigen-solves of the whole block are then done by
+    //      16 threads at once (one instruction stream instead of 16 redundant warp-wide ones)
+    __shared__ double eig_in[kKnnWarps][2][6];
+    __shared__ double eig_out[kKnnWarps][2][3];
+    const int cl = fa.k_lrf > 0 ? (fa.k_lrf < cnt ? fa.k_lrf : cnt) : 0;
+    const int rz = cl / 3;
+    const int cn = fa.k_nrm > 0 ? (fa.k_nrm < cnt ? fa.k_nrm : cnt) : 0;
     if (fa.k_lrf > 0) {
-        const int cl = fa.k_lrf < cnt ? fa.k_lrf : cnt;
-        const int rz = cl / 3;
-        const double radius = sqrt(W.d[cl - 1]);  // .cpp:256
         // .cpp:259-265 centroid of neighbours 1..rz-1 divided by rz
         double cx = 0, cy = 0, cz = 0;
 #pragma unroll
@@ -170,10 +234,63 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
             }
         }
 #pragma unroll
-        for (int e = 0; e < 6; e++) c6[e] = warp_sum(c6[e]);
-        double ev[3], V[3][3];
-        eig3_sym(c6, ev, V);  // .cpp:275-281
-        double zx = V[0][0], zy = V[1][0], zz = V[2][0];
+        for (int e = 0; e < 6; e++) {
+            double v = warp_sum(c6[e]);
+            if (lane == 0) eig_in[wib][0][e] = v;
+        }
+    }
+    if (fa.k_nrm > 0 && cn >= 3) {
+        // Open3D ComputeCovariance: cumulants over the neighbourhood including the point itself
+        double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            int j = lane + 32 * t;
+            if (j < cn) {
+                cu[0] += nx[t];
+                cu[1] += ny[t];
+                cu[2] += nz[t];
+                cu[3] += nx[t] * nx[t];
+                cu[4] += nx[t] * ny[t];
+                cu[5] += nx[t] * nz[t];
+                cu[6] += ny[t] * ny[t];
+                cu[7] += ny[t] * nz[t];
+                cu[8] += nz[t] * nz[t];
+            }
+        }
+        double invc = 1.0 / (double)cn;
+#pragma unroll
+        for (int e = 0; e < 9; e++) cu[e] = warp_sum(cu[e]) * invc;
+        if (lane == 0) {
+            eig_in[wib][1][0] = cu[3] - cu[0] * cu[0];
+            eig_in[wib][1][1] = cu[4] - cu[0] * cu[1];
+            eig_in[wib][1][2] = cu[5] - cu[0] * cu[2];
+            eig_in[wib][1][3] = cu[6] - cu[1] * cu[1];
+            eig_in[wib][1][4] = cu[7] - cu[1] * cu[2];
+            eig_in[wib][1][5] = cu[8] - cu[2] * cu[2];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kKnnWarps) {
+        int w = threadIdx.x >> 1, which = threadIdx.x & 1;
+        if ((which == 0 && fa.k_lrf > 0) || (which == 1 && fa.k_nrm > 0)) {
+            double a6[6], ev[3], V[3][3];
+#pragma unroll
+            for (int e = 0; e < 6; e++) a6[e] = eig_in[w][which][e];
+            eig3_sym(a6, ev, V);  // .cpp:275-281 / Open3D ComputeNormal: eigenvector of the smallest eigenvalue
+            eig_out[w][which][0] = V[0][0];
+            eig_out[w][which][1] = V[1][0];
+            eig_out[w][which][2] = V[2][0];
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+
+    if (fa.k_lrf > 0) {
+        key_t rad_bits;
+        int rad_id;
+        list_at(Ld, Li, cl - 1, rad_bits, rad_id);
+        const double radius = sqrt(__longlong_as_double((long long)rad_bits));  // .cpp:256
+        double zx = eig_out[wib][0][0], zy = eig_out[wib][0][1], zz = eig_out[wib][0][2];
         // .cpp:286-297
         double ax = 0, ay = 0, az = 0, wx = 0, wy = 0, wz = 0;
 #pragma unroll
@@ -218,56 +335,24 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
         }
     }
 
-    if (fa.k_nrm > 0) {
-        const int cn = fa.k_nrm < cnt ? fa.k_nrm : cnt;
-        double nvx = 0.0, nvy = 0.0, nvz = 1.0;
+    if (fa.k_nrm > 0 && lane == 0) {
+        double nvx = 0.0, nvy = 0.0, nvz = 1.0;  // fewer than 3 neighbours: Open3D's identity covariance -> (0,0,1)
         if (cn >= 3) {
-            // Open3D ComputeCovariance: cumulants over the neighbourhood including the point itself
-            double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                int j = lane + 32 * t;
-                if (j < cn) {
-                    cu[0] += nx[t];
-                    cu[1] += ny[t];
-                    cu[2] += nz[t];
-                    cu[3] += nx[t] * nx[t];
-                    cu[4] += nx[t] * ny[t];
-                    cu[5] += nx[t] * nz[t];
-                    cu[6] += ny[t] * ny[t];
-                    cu[7] += ny[t] * nz[t];
-                    cu[8] += nz[t] * nz[t];
-                }
-            }
-            double invc = 1.0 / (double)cn;
-#pragma unroll
-            for (int e = 0; e < 9; e++) cu[e] = warp_sum(cu[e]) * invc;
-            double c6[6];
-            c6[0] = cu[3] - cu[0] * cu[0];
-            c6[1] = cu[4] - cu[0] * cu[1];
-            c6[2] = cu[5] - cu[0] * cu[2];
-            c6[3] = cu[6] - cu[1] * cu[1];
-            c6[4] = cu[7] - cu[1] * cu[2];
-            c6[5] = cu[8] - cu[2] * cu[2];
-            double ev[3], V[3][3];
-            eig3_sym(c6, ev, V);
-            nvx = V[0][0], nvy = V[1][0], nvz = V[2][0];
+            nvx = eig_out[wib][1][0], nvy = eig_out[wib][1][1], nvz = eig_out[wib][1][2];
             if (nvx * nvx + nvy * nvy + nvz * nvz == 0.0) {
                 nvx = 0.0, nvy = 0.0, nvz = 1.0;
             }
         }
-        if (lane == 0) {
-            if (fa.nrm) {
-                fa.nrm[self] = nvx;
-                fa.nrm[n + self] = nvy;
-                fa.nrm[2 * n + self] = nvz;
-            }
-            if (fa.want_cov && fa.cov) {
-                double C6[6];
-                gicp_cov_from_normal(nvx, nvy, nvz, fa.gicp_eps, C6);
-                double* o = fa.cov + self;
-                for (int e = 0; e < 6; e++) o[e * n] = C6[e];
-            }
+        if (fa.nrm) {
+            fa.nrm[self] = nvx;
+            fa.nrm[n + self] = nvy;
+            fa.nrm[2 * n + self] = nvz;
+        }
+        if (fa.want_cov && fa.cov) {
+            double C6[6];
+            gicp_cov_from_normal(nvx, nvy, nvz, fa.gicp_eps, C6);
+            double* o = fa.cov + self;
+            for (int e = 0; e < 6; e++) o[e * n] = C6[e];
         }
     }
 }

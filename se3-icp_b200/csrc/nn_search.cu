@@ -250,7 +250,7 @@ int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConf
 // ------------------------------------------------------------------------------------------------
 constexpr int kTreeWarps = 8;
 
-__global__ void __launch_bounds__(kTreeWarps * 32) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
+__global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                                        IterState* __restrict__ state, CorrBuffers cb) {
     if (state->done || !se3_phase_active(cfg, state)) return;
     __shared__ int2 stacks[kTreeWarps][kStackEntries];
@@ -266,12 +266,15 @@ __global__ void __launch_bounds__(kTreeWarps * 32) nn_se3_tree_kernel(SourceView
 
     double q[12];
     make_query(S, cfg, Tm, i, q);
-    float qlo[12], qhi[12];
+    // FP32 query with one scalar margin covering its rounding: |q_k - qf_k| <= 2^-24 |q_k| <= qeps
+    float qf[12];
+    float qamax = 0.f;
 #pragma unroll
     for (int k = 0; k < 12; k++) {
-        qlo[k] = __double2float_rd(q[k]);
-        qhi[k] = __double2float_ru(q[k]);
+        qf[k] = (float)q[k];
+        qamax = fmaxf(qamax, fabsf(qf[k]));
     }
+    const float qeps = qamax * 1.1920929e-07f;  // 2^-23 |q|max: twice the worst rounding of any coordinate
     // rigorous FP32 lower bound: every operation rounds toward the smaller result
     auto lb_fn = [&](int node) -> double {
         const float* b = T.box12 + node;
@@ -279,7 +282,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) nn_se3_tree_kernel(SourceView
 #pragma unroll
         for (int k = 0; k < 12; k++) {
             float lo = b[(size_t)k * tn], hi = b[(size_t)(12 + k) * tn];
-            float d = fmaxf(0.f, fmaxf(__fsub_rd(lo, qhi[k]), __fsub_rd(qlo[k], hi)));
+            float d = fmaxf(__fsub_rd(lo, qf[k]), __fsub_rd(qf[k], hi));
+            d = fmaxf(0.f, __fsub_rd(d, qeps));
             acc = __fadd_rd(acc, __fmul_rd(d, d));
         }
         return (double)acc;
@@ -295,15 +299,15 @@ __global__ void __launch_bounds__(kTreeWarps * 32) nn_se3_tree_kernel(SourceView
             d2 = exact_d2_12(q, T.rows64, m, p);
             id = T.perm12[p];
         }
+        // warm-started searches rarely improve: only reduce across the warp when some lane beats tau
+        if (__ballot_sync(SE3_FULL, d2 < tau || (d2 == tau && id < best_id)) == 0u) return;
         double wd = d2;
         int wid = id;
         warp_argmin(wd, wid);
-        if (wd < tau || (wd == tau && wid < best_id)) {
-            unsigned who = __ballot_sync(SE3_FULL, id == wid && d2 == wd);
-            tau = wd;
-            best_id = wid;
-            best_j = leaf * 32 + (__ffs(who) - 1);
-        }
+        unsigned who = __ballot_sync(SE3_FULL, id == wid && d2 == wd);
+        tau = wd;
+        best_id = wid;
+        best_j = leaf * 32 + (__ffs(who) - 1);
     };
 
     int prev = cb.idx[i];
@@ -375,11 +379,10 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
             d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
             id = I.perm[p];
         }
+        if (__ballot_sync(SE3_FULL, d2 < tau || (d2 == tau && id < best)) == 0u) return;
         warp_argmin(d2, id);
-        if (d2 < tau || (d2 == tau && id < best)) {
-            tau = d2;
-            best = id;
-        }
+        tau = d2;
+        best = id;
     };
 
     int prev = cb.idx[i];
