@@ -137,10 +137,19 @@ int se3icp_run_batch_device(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const dou
                             const double* const* d_tgt, const size_t* n_tgt, const se3icp_params* p, double* T_out,
                             se3icp_stats* stats);
 
-/* one very large pair: target replicated, source range [src_begin, src_end) owned by this rank;
- * the 6x6 system is all-reduced over nccl_comm (an ncclComm_t) every iteration. */
+/* one very large pair (BASELINE.json configs[4]): every rank holds both clouds (se3icp_set_cloud), owns the
+ * source query range [src_begin, src_end) for LRF set-up, correspondence search and reduction, and the
+ * 29-double normal-equation record is all-reduced once per iteration (plus 4 x 256-bin histograms when the
+ * trimmed rejection is active).  All ranks return the identical transform.
+ * The communicator is either created by the library (se3icp_comm_unique_id on one rank, broadcast the
+ * SE3ICP_COMM_ID_BYTES by any means, se3icp_comm_init on every rank; pass nccl_comm = NULL) or supplied by
+ * the caller as an ncclComm_t with its rank / size.  NCCL is resolved at run time (dlopen libnccl.so.2). */
+#define SE3ICP_COMM_ID_BYTES 128
+int se3icp_comm_unique_id(void* id_out);
+int se3icp_comm_init(se3icp_ctx* ctx, int n_ranks, int rank, const void* id);
+int se3icp_comm_destroy(se3icp_ctx* ctx);
 int se3icp_run_sharded(se3icp_ctx* ctx, const se3icp_params* p, size_t src_begin, size_t src_end, void* nccl_comm,
-                       double* T_out, se3icp_stats* stats);
+                       int rank, int n_ranks, double* T_out, se3icp_stats* stats);
 
 /* measurement hook (bench.py roofline): re-launches one kernel of the hot path `repeats` times on the
  * context's stream, on the device data left by the last se3icp_run, and returns the average launch

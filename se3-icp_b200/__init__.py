@@ -5,5 +5,5 @@ host/          C++17 host class with the reference's declaration, calling the C 
 capi.py        ctypes binding of the C ABI
 registration.py  Python mirror of IterativeSE3Registration (same names / defaults / error behaviour)
 """
-from . import capi  # noqa: F401
+from . import capi, sharding  # noqa: F401
 from .registration import IterativeSE3Registration, run_registration_method, METHODS  # noqa: F401

@@ -18,6 +18,7 @@ SOURCE, TARGET = 0, 1
 STAGE_NN_SE3, STAGE_NN_XYZ, STAGE_REDUCE, STAGE_KNN_TARGET = 0, 1, 2, 3
 VARIANTS = {"pt2pt": PT2PT, "pt2pl": PT2PL, "gicp": GICP}
 MAX_KNN = 128
+COMM_ID_BYTES = 128
 
 STATUS = {0: "OK", 1: "ERR_ARG", 2: "ERR_NO_DEVICE", 3: "ERR_CUDA", 4: "ERR_NCCL", 5: "ERR_UNSUPPORTED", 6: "ERR_STATE"}
 
@@ -70,7 +71,8 @@ EXPORTED_SYMBOLS = [
     "se3icp_abi_version", "se3icp_last_error", "se3icp_default_params", "se3icp_create", "se3icp_destroy",
     "se3icp_synchronize", "se3icp_set_cloud", "se3icp_set_cloud_device", "se3icp_run", "se3icp_run_async",
     "se3icp_run_finish", "se3icp_get_history", "se3icp_get_correspondences", "se3icp_get_se3_cloud",
-    "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_run_sharded", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
+    "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_run_sharded", "se3icp_comm_unique_id", "se3icp_comm_init",
+    "se3icp_comm_destroy", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
     "se3icp_normals", "se3icp_gicp_cov", "se3icp_nn_se3", "se3icp_nn_xyz", "se3icp_trim", "se3icp_reduce_pt2pt",
     "se3icp_reduce_pt2pl", "se3icp_reduce_gicp", "se3icp_solve",
 ]
@@ -197,6 +199,23 @@ class Context:
         _check(lib().se3icp_get_se3_cloud(self._h, int(which), _dp(fr), C.c_size_t(n)))
         return fr
 
+    # ---- one large pair sharded over ranks --------------------------------------------------------
+    def comm_init(self, n_ranks, rank, comm_id):
+        """comm_id: the COMM_ID_BYTES produced by comm_unique_id() on one rank and broadcast to all"""
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        _check(lib().se3icp_comm_init(self._h, int(n_ranks), int(rank), buf))
+
+    def comm_destroy(self):
+        _check(lib().se3icp_comm_destroy(self._h))
+
+    def run_sharded(self, params, src_begin, src_end, nccl_comm=None, rank=0, n_ranks=1):
+        T = np.zeros((4, 4))
+        st = Stats()
+        _check(lib().se3icp_run_sharded(self._h, C.byref(params), C.c_size_t(src_begin), C.c_size_t(src_end),
+                                        C.c_void_p(nccl_comm) if nccl_comm else None, int(rank), int(n_ranks), _dp(T),
+                                        C.byref(st)))
+        return T, st
+
     def time_stage(self, stage, repeats=10):
         """average launch duration (ms) of one hot-path kernel on the data of the last run (CUDA events)"""
         ms = C.c_double(0)
@@ -291,6 +310,12 @@ class Context:
         T = np.zeros((4, 4))
         _check(lib().se3icp_solve(self._h, _dp(in27), _dp(T)))
         return T
+
+
+def comm_unique_id():
+    buf = (C.c_char * COMM_ID_BYTES)()
+    _check(lib().se3icp_comm_unique_id(buf))
+    return bytes(buf)
 
 
 def run_batch(ctxs, pairs, params, device_inputs=False):

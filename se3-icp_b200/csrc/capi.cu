@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "context.h"
 #include "internal.h"
+#include "nccl_dyn.h"
 
 namespace se3 {
 
@@ -73,6 +74,8 @@ using namespace se3;
 SourceView se3icp_ctx::source_view() const {
     SourceView S;
     S.n = (int)n[0];
+    S.begin = sharded ? shard_begin : 0;
+    S.end = sharded ? shard_end : (int)n[0];
     S.x = index[0].x.as<double>();
     S.y = index[0].y.as<double>();
     S.z = index[0].z.as<double>();
@@ -183,8 +186,20 @@ int alloc_run(se3icp_ctx* c) {
     SE3_TRY(c->block_eq.ensure((size_t)kReduceBlocks * sizeof(int)));
     if (cfg.record_history) SE3_TRY(c->history.ensure((size_t)cfg.max_history * 16 * sizeof(double)));
     SE3_TRY(c->state.ensure(sizeof(IterState)));
+    SE3_TRY(c->totals.ensure(kReducePartials * sizeof(double)));
+    SE3_TRY(c->eq_total.ensure(sizeof(int)));
+    SE3_TRY(c->rank_eq.ensure((size_t)std::max(c->comm_size, 1) * sizeof(int)));
     return 0;
 }
+
+#define SE3_NCCL(call)                                                                        \
+    do {                                                                                      \
+        ncclResult_t r__ = (call);                                                            \
+        if (r__ != ncclSuccess) {                                                             \
+            set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl->GetErrorString(r__)); \
+            return SE3ICP_ERR_NCCL;                                                           \
+        }                                                                                     \
+    } while (0)
 
 int enqueue_setup(se3icp_ctx* c) {
     const RunConfig& cfg = c->cfg;
@@ -238,6 +253,12 @@ int enqueue_setup(se3icp_ctx* c) {
         fa.nrm = c->nrm[w].as<double>();
         fa.cov = c->cov[w].as<double>();
         fa.K = std::max(fa.k_lrf, fa.k_nrm);
+        fa.q_begin = 0;
+        fa.q_end = 0x7fffffff;
+        if (w == 0 && c->sharded) {  // source features are only needed for this rank's query range
+            fa.q_begin = c->shard_begin;
+            fa.q_end = c->shard_end;
+        }
         if (fa.K <= 0) continue;
         SE3_TRY(launch_knn_features(c->index[w].view, fa, st));
         c->launches += 1;
@@ -272,13 +293,46 @@ int enqueue_iteration(se3icp_ctx* c) {
         SE3_TRY(launch_nn_xyz(S, T, cfg, ds, cb, st));
         c->launches += 1;
     }
+    const bool multi = c->sharded && c->comm && c->comm_size > 1;
+    const NcclApi* nccl = multi ? nccl_api() : nullptr;
+    if (multi && !nccl) return SE3ICP_ERR_NCCL;
+    ncclComm_t comm = (ncclComm_t)c->comm;
     if (cfg.trim_active && cfg.n_keep_target > 0) {
-        SE3_TRY(launch_trim(cfg, ds, cb, S.n, c->hist.as<unsigned int>(), c->block_eq.as<int>(), st));
+        if (!c->sharded) {
+            SE3_TRY(launch_trim(cfg, ds, cb, S.n, c->hist.as<unsigned int>(), c->block_eq.as<int>(), st));
+        } else {
+            // global threshold: every radix pass all-reduces its 256-bin histogram; ties at the
+            // threshold are granted in global index order (lower ranks first)
+            const float* df = cb.distf + S.begin;
+            int nl = S.end - S.begin;
+            unsigned int* hist = c->hist.as<unsigned int>();
+            for (int pass = 0; pass < 4; pass++) {
+                SE3_TRY(launch_trim_hist(cfg, ds, df, nl, hist, pass, st));
+                if (multi) SE3_NCCL(nccl->AllReduce(hist + pass * 256, hist + pass * 256, 256, ncclUint32, ncclSum, comm, st));
+            }
+            SE3_CUDA(cudaMemsetAsync(c->eq_total.ptr, 0, sizeof(int), st));
+            SE3_TRY(launch_trim_count_eq(cfg, ds, df, nl, hist, c->block_eq.as<int>(), c->eq_total.as<int>(), st));
+            const int* rank_eq = nullptr;
+            if (multi) {
+                SE3_NCCL(nccl->AllGather(c->eq_total.ptr, c->rank_eq.ptr, 1, ncclInt32, comm, st));
+                rank_eq = c->rank_eq.as<int>();
+            }
+            SE3_TRY(launch_trim_apply(cfg, ds, df, nl, hist, c->block_eq.as<int>(), rank_eq, c->comm_rank, cb.keep + S.begin, st));
+        }
         c->launches += 6;
     }
     SE3_TRY(launch_reduce(S, T, cfg, ds, cb, c->partials.as<double>(), st));
-    SE3_TRY(launch_solve_update(cfg, ds, c->partials.as<double>(), c->history.as<double>(), c->hist.as<unsigned int>(), st));
-    c->launches += 2;
+    if (multi) {
+        // one all-reduce of the 29-double record per iteration; every rank then runs the identical solve
+        SE3_TRY(launch_sum_partials(c->partials.as<double>(), c->totals.as<double>(), st));
+        SE3_NCCL(nccl->AllReduce(c->totals.ptr, c->totals.ptr, kReducePartials, ncclFloat64, ncclSum, comm, st));
+        SE3_TRY(launch_solve_update(cfg, ds, c->totals.as<double>(), 1, c->history.as<double>(), c->hist.as<unsigned int>(), st));
+        c->launches += 3;
+    } else {
+        SE3_TRY(launch_solve_update(cfg, ds, c->partials.as<double>(), kReduceBlocks, c->history.as<double>(),
+                                    c->hist.as<unsigned int>(), st));
+        c->launches += 2;
+    }
     return 0;
 }
 
@@ -365,6 +419,7 @@ int se3icp_destroy(se3icp_ctx* c) {
     if (!c) return SE3ICP_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && c->comm_owned) se3icp_comm_destroy(c);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -411,8 +466,15 @@ int se3icp_set_cloud_device(se3icp_ctx* c, int which, const double* d_xyz, size_
     return SE3ICP_OK;
 }
 
+static int run_async_impl(se3icp_ctx* c, const se3icp_params* p);
+
 int se3icp_run_async(se3icp_ctx* c, const se3icp_params* p) {
     SE3_TRY(check_ctx(c));
+    c->sharded = false;
+    return run_async_impl(c, p);
+}
+
+static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     if (!p) return SE3ICP_ERR_ARG;
     if (c->n[0] == 0 || c->n[1] == 0 || !c->raw_view[0] || !c->raw_view[1]) {
         set_last_error("source/target cloud not set");
@@ -595,11 +657,72 @@ int se3icp_run_batch_device(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const dou
     return run_batch_impl(ctxs, n_ctx, n_pairs, d_src, n_src, d_tgt, n_tgt, p, T_out, stats, true);
 }
 
+int se3icp_comm_unique_id(void* id) {
+    if (!id) return SE3ICP_ERR_ARG;
+    const NcclApi* nccl = nccl_api();
+    if (!nccl) return SE3ICP_ERR_NCCL;
+    ncclUniqueId uid;
+    SE3_NCCL(nccl->GetUniqueId(&uid));
+    static_assert(sizeof(ncclUniqueId) == SE3ICP_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &uid, sizeof(uid));
+    return SE3ICP_OK;
+}
+
+int se3icp_comm_init(se3icp_ctx* c, int n_ranks, int rank, const void* id) {
+    SE3_TRY(check_ctx(c));
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return SE3ICP_ERR_ARG;
+    const NcclApi* nccl = nccl_api();
+    if (!nccl) return SE3ICP_ERR_NCCL;
+    if (c->comm && c->comm_owned) nccl->CommDestroy((ncclComm_t)c->comm);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm;
+    SE3_NCCL(nccl->CommInitRank(&comm, n_ranks, uid, rank));
+    c->comm = comm;
+    c->comm_owned = true;
+    c->comm_rank = rank;
+    c->comm_size = n_ranks;
+    return SE3ICP_OK;
+}
+
+int se3icp_comm_destroy(se3icp_ctx* c) {
+    SE3_TRY(check_ctx(c));
+    if (c->comm && c->comm_owned) {
+        const NcclApi* nccl = nccl_api();
+        if (nccl) nccl->CommDestroy((ncclComm_t)c->comm);
+    }
+    c->comm = nullptr;
+    c->comm_owned = false;
+    c->comm_rank = 0;
+    c->comm_size = 1;
+    return SE3ICP_OK;
+}
+
 int se3icp_run_sharded(se3icp_ctx* c, const se3icp_params* p, size_t src_begin, size_t src_end, void* nccl_comm,
-                       double* T_out, se3icp_stats* stats) {
-    (void)c, (void)p, (void)src_begin, (void)src_end, (void)nccl_comm, (void)T_out, (void)stats;
-    set_last_error("se3icp_run_sharded: not built yet");
-    return SE3ICP_ERR_UNSUPPORTED;
+                       int rank, int n_ranks, double* T_out, se3icp_stats* stats) {
+    SE3_TRY(check_ctx(c));
+    if (src_begin > src_end || src_end > c->n[0]) {
+        set_last_error("bad source range [%zu, %zu) of %zu", src_begin, src_end, c->n[0]);
+        return SE3ICP_ERR_ARG;
+    }
+    if (nccl_comm) {  // caller-owned communicator
+        if (c->comm && c->comm_owned) se3icp_comm_destroy(c);
+        c->comm = nccl_comm;
+        c->comm_owned = false;
+        c->comm_rank = rank;
+        c->comm_size = n_ranks;
+    }
+    if (!c->comm && (src_begin != 0 || src_end != c->n[0])) {
+        set_last_error("a partial source range needs a communicator (se3icp_comm_init)");
+        return SE3ICP_ERR_STATE;
+    }
+    c->sharded = true;
+    c->shard_begin = (int)src_begin;
+    c->shard_end = (int)src_end;
+    int rc = run_async_impl(c, p);
+    if (rc == SE3ICP_OK) rc = se3icp_run_finish(c, T_out, stats);
+    c->sharded = false;
+    return rc;
 }
 
 int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
@@ -655,6 +778,8 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
                 fa.nrm = c->nrm[1].as<double>();
                 fa.cov = c->cov[1].as<double>();
                 fa.K = std::max(fa.k_lrf, fa.k_nrm);
+                fa.q_begin = 0;
+                fa.q_end = 0x7fffffff;
                 if (fa.K <= 0) return SE3ICP_ERR_STATE;
                 SE3_TRY(launch_knn_features(c->index[1].view, fa, st));
             }
@@ -730,6 +855,8 @@ int stage_features(se3icp_ctx* c, const double* xyz, size_t n, int k_lrf, int k_
     fa.k_lrf = k_lrf;
     fa.k_nrm = k_nrm;
     fa.K = k_list;
+    fa.q_begin = 0;
+    fa.q_end = 0x7fffffff;
     if (k_lrf > 0) {
         SE3_TRY(c->frame[0].ensure(9 * n * sizeof(double)));
         fa.frame = c->frame[0].as<double>();
@@ -855,6 +982,8 @@ int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double*
     c->n[0] = n;
     SourceView S{};
     S.n = (int)n;
+    S.begin = 0;
+    S.end = (int)n;
     S.x = c->scratch.as<double>();
     S.y = S.x + n;
     S.z = S.x + 2 * n;
@@ -897,6 +1026,8 @@ int se3icp_nn_xyz(se3icp_ctx* c, const double* queries, size_t n, const double* 
     c->n[0] = n;
     SourceView S{};
     S.n = (int)n;
+    S.begin = 0;
+    S.end = (int)n;
     S.x = c->scratch.as<double>();
     S.y = S.x + n;
     S.z = S.x + 2 * n;
@@ -964,6 +1095,8 @@ int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* sr
     c->n[0] = n;
     SourceView S{};
     S.n = (int)n;
+    S.begin = 0;
+    S.end = (int)n;
     S.x = c->scratch.as<double>();
     S.y = S.x + n;
     S.z = S.x + 2 * n;
@@ -985,7 +1118,7 @@ int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* sr
         }
     }
     if (T_out) {
-        SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), nullptr, c->hist.as<unsigned int>(), c->stream));
+        SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), kReduceBlocks, nullptr, c->hist.as<unsigned int>(), c->stream));
         SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
         SE3_CUDA(cudaStreamSynchronize(c->stream));
         memcpy(T_out, c->h_state->T_i, 16 * sizeof(double));
@@ -1030,7 +1163,7 @@ int se3icp_solve(se3icp_ctx* c, const double* in27, double* T_out) {
     SE3_CUDA(cudaMemcpyAsync(c->partials.ptr, part.data(), part.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     RunConfig cfg;
     identity_config(cfg, SE3ICP_PT2PL, false);
-    SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), nullptr, c->hist.as<unsigned int>(), c->stream));
+    SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), kReduceBlocks, nullptr, c->hist.as<unsigned int>(), c->stream));
     SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
     SE3_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(T_out, c->h_state->T_i, 16 * sizeof(double));

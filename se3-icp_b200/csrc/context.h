@@ -24,6 +24,14 @@ struct se3icp_ctx {
     se3::DeviceBuf partials, hist, block_eq, history;
     se3::DeviceBuf state;
     se3::DeviceBuf scratch;  // stage-level API staging
+    se3::DeviceBuf totals, eq_total, rank_eq;  // sharded pair: all-reduced record, threshold-tie counts
+
+    // one very large pair sharded over ranks (se3icp_run_sharded)
+    void* comm = nullptr;  // ncclComm_t
+    bool comm_owned = false;
+    int comm_rank = 0, comm_size = 1;
+    bool sharded = false;
+    int shard_begin = 0, shard_end = 0;
 
     se3::IterState* h_state = nullptr;  // pinned
     int* h_flag = nullptr;              // pinned

@@ -91,7 +91,8 @@ struct RunConfig {
 };
 
 struct SourceView {
-    int n;
+    int n;                // points in the cloud (plane stride of frame / cov)
+    int begin, end;       // query range owned by this rank: [0, n) unless the pair is sharded
     const double* x;      // working-frame original coordinates p0 (never rewritten: q = T_total * p0 on the fly)
     const double* y;
     const double* z;
@@ -150,6 +151,7 @@ struct FeatureArgs {
     int* knn_idx;     // optional [n*K] (stage API), original order rows
     double* knn_d2;   // optional [n*K]
     int K;            // list length = max(k_lrf, k_nrm, requested)
+    int q_begin, q_end;  // only points whose ORIGINAL index lies in [q_begin, q_end) are processed (sharded source)
 };
 int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t st);
 int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, double* cov /*[6][n]*/, cudaStream_t st);
@@ -167,9 +169,17 @@ int launch_nn_xyz(const SourceView& S, const TargetView& T, const RunConfig& cfg
 // optimise.cu
 int launch_trim(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, unsigned int* hist /*[4*256]*/,
                 int* block_eq /*[kReduceBlocks]*/, cudaStream_t st);
+int launch_trim_hist(const RunConfig& cfg, IterState* state, const float* distf, int n, unsigned int* hist, int pass,
+                     cudaStream_t st);
+int launch_trim_count_eq(const RunConfig& cfg, IterState* state, const float* distf, int n, const unsigned int* hist,
+                         int* block_eq, int* eq_total, cudaStream_t st);
+int launch_trim_apply(const RunConfig& cfg, IterState* state, const float* distf, int n, const unsigned int* hist,
+                      const int* block_eq, const int* rank_eq, int rank, uint8_t* keep, cudaStream_t st);
 int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                   double* partials /*[kReduceBlocks*kReducePartials]*/, cudaStream_t st);
-int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, double* history,
+int launch_sum_partials(const double* partials /*[kReduceBlocks][kReducePartials]*/, double* total /*[kReducePartials]*/,
+                        cudaStream_t st);
+int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,
                         unsigned int* hist /*[4*256] trim histograms, zeroed for the next iteration*/, cudaStream_t st);
 int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st);
 int launch_init_state(IterState* state, unsigned int* hist, cudaStream_t st);

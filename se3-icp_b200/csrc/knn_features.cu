@@ -97,12 +97,16 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     // query = Morton position s.  Warps past the end redo the last query without writing, so the whole
     // block reaches the __syncthreads() of the batched eigen-solves below.
     const int s_raw = blockIdx.x * kKnnWarps + wib;
-    const bool active = s_raw < I.n;
-    const int s = active ? s_raw : I.n - 1;
+    const bool in_range = s_raw < I.n;
+    const int s = in_range ? s_raw : I.n - 1;
     KnnScratch& W = scratch[wib];
 
     const double qx = I.sx[s], qy = I.sy[s], qz = I.sz[s];
     const int self = I.perm[s];
+    // sharded source: only the rank's own range of original indices is processed; block-uniform exit
+    // is not possible (neighbouring Morton positions belong to different ranks), so foreign queries
+    // fall through as inactive warps
+    const bool active = in_range && self >= fa.q_begin && self < fa.q_end;
     const int K = fa.K < I.n ? fa.K : I.n;
     key_t Ld[4] = {kInfKey, kInfKey, kInfKey, kInfKey};
     int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
@@ -158,14 +162,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     const int half = (K + 63) / 64;
     const int w0 = L - half > 0 ? L - half : 0;
     const int w1 = L + half < n_leaves - 1 ? L + half : n_leaves - 1;
-    for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
-    while (pend > 0) flush32();
-
-    traverse_boxes(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
-        if (leaf >= w0 && leaf <= w1) return;
-        eval_leaf(leaf);
-    });
-    while (pend > 0) flush32();
+    if (active) {
+        for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
+        while (pend > 0) flush32();
+        traverse_boxes(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
+            if (leaf >= w0 && leaf <= w1) return;
+            eval_leaf(leaf);
+        });
+        while (pend > 0) flush32();
+    }
     const int cnt = K;  // the list now holds the min(K, n) nearest, ascending, then padding
 
     if (fa.knn_idx && active) {
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     for (int t = 0; t < 4; t++) {
         int j = lane + 32 * t;
         nx[t] = ny[t] = nz[t] = 0.0;
-        if (j < cnt) {
+        if (j < cnt && active) {
             int id = Li[t];
             nx[t] = I.x[id];
             ny[t] = I.y[id];
@@ -199,10 +204,12 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     //      16 threads at once (one instruction stream instead of 16 redundant warp-wide ones)
     __shared__ double eig_in[kKnnWarps][2][6];
     __shared__ double eig_out[kKnnWarps][2][3];
+    __shared__ int eig_valid[kKnnWarps];
+    if (lane == 0) eig_valid[wib] = active ? 1 : 0;
     const int cl = fa.k_lrf > 0 ? (fa.k_lrf < cnt ? fa.k_lrf : cnt) : 0;
     const int rz = cl / 3;
     const int cn = fa.k_nrm > 0 ? (fa.k_nrm < cnt ? fa.k_nrm : cnt) : 0;
-    if (fa.k_lrf > 0) {
+    if (fa.k_lrf > 0 && active) {
         // .cpp:259-265 centroid of neighbours 1..rz-1 divided by rz
         double cx = 0, cy = 0, cz = 0;
 #pragma unroll
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
             if (lane == 0) eig_in[wib][0][e] = v;
         }
     }
-    if (fa.k_nrm > 0 && cn >= 3) {
+    if (fa.k_nrm > 0 && cn >= 3 && active) {
         // Open3D ComputeCovariance: cumulants over the neighbourhood including the point itself
         double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     __syncthreads();
     if (threadIdx.x < 2 * kKnnWarps) {
         int w = threadIdx.x >> 1, which = threadIdx.x & 1;
-        if ((which == 0 && fa.k_lrf > 0) || (which == 1 && fa.k_nrm > 0)) {
+        if (eig_valid[w] && ((which == 0 && fa.k_lrf > 0) || (which == 1 && fa.k_nrm > 0))) {
             double a6[6], ev[3], V[3][3];
 #pragma unroll
             for (int e = 0; e < 6; e++) a6[e] = eig_in[w][which][e];

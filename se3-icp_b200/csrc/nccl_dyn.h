@@ -1,0 +1,22 @@
+// nccl_dyn.h — NCCL resolved at run time (dlopen), so libse3icp_cuda.so has no link-time dependency
+// on a particular libnccl and shares the copy already loaded in the process (e.g. PyTorch's).
+#pragma once
+
+#include <nccl.h>  // types and enums only
+
+namespace se3 {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+// returns nullptr (and sets the last error) when no libnccl can be loaded
+const NcclApi* nccl_api();
+
+}  // namespace se3

@@ -89,10 +89,10 @@ __global__ void __launch_bounds__(kBfThreads) nn_se3_brute_kernel(SourceView S, 
     int qi[kBfQ];
 #pragma unroll
     for (int u = 0; u < kBfQ; u++) {
-        qi[u] = blockIdx.x * (kBfThreads * kBfQ) + u * kBfThreads + threadIdx.x;
+        qi[u] = S.begin + blockIdx.x * (kBfThreads * kBfQ) + u * kBfThreads + threadIdx.x;
         b1[u] = b2[u] = 3.0e38f;
         i1[u] = 0;
-        if (qi[u] < S.n) {
+        if (qi[u] < S.end) {
             double q[12];
             make_query(S, cfg, Tm, qi[u], q);
 #pragma unroll
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kBfThreads) nn_se3_brute_kernel(SourceView S, 
 #pragma unroll
     for (int u = 0; u < kBfQ; u++) {
         int i = qi[u];
-        if (i >= S.n) continue;
+        if (i >= S.end) continue;
         double q[12];
         make_query(S, cfg, Tm, i, q);
         double amax = 0.0;
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(kBfThreads) nn_se3_brute_kernel(SourceView S, 
 int launch_nn_se3_brute(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                         int force_all_repair, cudaStream_t st) {
     int per_block = kBfThreads * kBfQ;
-    int g = (S.n + per_block - 1) / per_block;
+    int g = (S.end - S.begin + per_block - 1) / per_block;
+    if (g < 1) g = 1;
     nn_se3_brute_kernel<<<g, kBfThreads, 0, st>>>(S, T, cfg, state, cb, force_all_repair);
     SE3_CUDA(cudaGetLastError());
     return 0;
@@ -241,7 +242,8 @@ __global__ void __launch_bounds__(kRepairThreads) nn_se3_repair_kernel(SourceVie
 
 int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                          cudaStream_t st) {
-    int g = S.n < 148 * 4 ? (S.n > 0 ? S.n : 1) : 148 * 4;
+    int cnt = S.end - S.begin;
+    int g = cnt < 148 * 4 ? (cnt > 0 ? cnt : 1) : 148 * 4;
     nn_se3_repair_kernel<<<g, kRepairThreads, 0, st>>>(S, T, cfg, state, cb);
     SE3_CUDA(cudaGetLastError());
     return 0;
@@ -258,8 +260,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * kTreeWarps + wib;
-    if (i >= S.n) return;
+    const int i = S.begin + blockIdx.x * kTreeWarps + wib;
+    if (i >= S.end) return;
     const int M = T.n;
     const size_t m = (size_t)M, tn = (size_t)T.idx.total_nodes;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -341,7 +343,8 @@ int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig
         set_last_error("cloud too large for the traversal stack");
         return SE3ICP_ERR_UNSUPPORTED;
     }
-    int g = (S.n + kTreeWarps - 1) / kTreeWarps;
+    int g = (S.end - S.begin + kTreeWarps - 1) / kTreeWarps;
+    if (g < 1) g = 1;
     nn_se3_tree_kernel<<<g, kTreeWarps * 32, 0, st>>>(S, T, cfg, state, cb);
     SE3_CUDA(cudaGetLastError());
     return 0;
@@ -358,8 +361,8 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * kXyzWarps + wib;
-    if (i >= S.n) return;
+    const int i = S.begin + blockIdx.x * kXyzWarps + wib;
+    if (i >= S.end) return;
     const CloudIndex& I = T.idx;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
@@ -417,7 +420,8 @@ int launch_nn_xyz(const SourceView& S, const TargetView& T, const RunConfig& cfg
         set_last_error("cloud too large for the traversal stack");
         return SE3ICP_ERR_UNSUPPORTED;
     }
-    int g = (S.n + kXyzWarps - 1) / kXyzWarps;
+    int g = (S.end - S.begin + kXyzWarps - 1) / kXyzWarps;
+    if (g < 1) g = 1;
     nn_xyz_kernel<<<g, kXyzWarps * 32, 0, st>>>(S, T, cfg, state, cb);
     SE3_CUDA(cudaGetLastError());
     return 0;

@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(256) trim_hist_kernel(RunConfig cfg, const Ite
 // chunked, order-preserving: block b owns elements [b*chunk, (b+1)*chunk)
 __global__ void __launch_bounds__(256) trim_count_eq_kernel(RunConfig cfg, const IterState* __restrict__ state,
                                                              const float* __restrict__ distf, int n,
-                                                             const unsigned int* __restrict__ hist, int* __restrict__ block_eq) {
+                                                             const unsigned int* __restrict__ hist, int* __restrict__ block_eq,
+                                                             int* __restrict__ eq_total) {
     if (state->done) return;
     __shared__ unsigned int s_thr;
     __shared__ int s_cnt[8];
@@ -171,13 +172,14 @@ __global__ void __launch_bounds__(256) trim_count_eq_kernel(RunConfig cfg, const
         int t = 0;
         for (int k = 0; k < 8; k++) t += s_cnt[k];
         block_eq[blockIdx.x] = t;
+        if (eq_total && t) atomicAdd(eq_total, t);  // integer sum: order-independent
     }
 }
 
 __global__ void __launch_bounds__(256) trim_apply_kernel(RunConfig cfg, IterState* __restrict__ state,
                                                           const float* __restrict__ distf, int n,
                                                           const unsigned int* __restrict__ hist, const int* __restrict__ block_eq,
-                                                          uint8_t* __restrict__ keep) {
+                                                          const int* __restrict__ rank_eq, int rank, uint8_t* __restrict__ keep) {
     if (state->done) return;
     __shared__ unsigned int s_thr, s_budget;
     __shared__ int s_base;
@@ -189,6 +191,8 @@ __global__ void __launch_bounds__(256) trim_apply_kernel(RunConfig cfg, IterStat
             s_thr = prefix;
             s_budget = krem + 1;  // how many of the elements equal to the threshold survive
             int base = 0;
+            if (rank_eq)  // sharded pair: threshold ties owned by lower ranks come first in index order
+                for (int r = 0; r < rank; r++) base += rank_eq[r];
             for (int b = 0; b < (int)blockIdx.x; b++) base += block_eq[b];
             s_base = base;
             if (blockIdx.x == 0) {
@@ -224,15 +228,36 @@ __global__ void __launch_bounds__(256) trim_apply_kernel(RunConfig cfg, IterStat
     }
 }
 
+int launch_trim_hist(const RunConfig& cfg, IterState* state, const float* distf, int n, unsigned int* hist, int pass,
+                     cudaStream_t st) {
+    int g = (n + 255) / 256;
+    if (g > 148 * 4) g = 148 * 4;
+    if (g < 1) g = 1;
+    trim_hist_kernel<<<g, 256, 0, st>>>(cfg, state, distf, n, hist, pass);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_trim_count_eq(const RunConfig& cfg, IterState* state, const float* distf, int n, const unsigned int* hist,
+                         int* block_eq, int* eq_total, cudaStream_t st) {
+    trim_count_eq_kernel<<<kReduceBlocks, 256, 0, st>>>(cfg, state, distf, n, hist, block_eq, eq_total);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_trim_apply(const RunConfig& cfg, IterState* state, const float* distf, int n, const unsigned int* hist,
+                      const int* block_eq, const int* rank_eq, int rank, uint8_t* keep, cudaStream_t st) {
+    trim_apply_kernel<<<kReduceBlocks, 256, 0, st>>>(cfg, state, distf, n, hist, block_eq, rank_eq, rank, keep);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_trim(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, unsigned int* hist, int* block_eq,
                 cudaStream_t st) {
     if (!cfg.trim_active) return 0;
-    int g = (n + 255) / 256;
-    if (g > 148 * 4) g = 148 * 4;
-    for (int pass = 0; pass < 4; pass++) trim_hist_kernel<<<g, 256, 0, st>>>(cfg, state, cb.distf, n, hist, pass);
-    trim_count_eq_kernel<<<kReduceBlocks, 256, 0, st>>>(cfg, state, cb.distf, n, hist, block_eq);
-    trim_apply_kernel<<<kReduceBlocks, 256, 0, st>>>(cfg, state, cb.distf, n, hist, block_eq, cb.keep);
-    SE3_CUDA(cudaGetLastError());
+    for (int pass = 0; pass < 4; pass++) SE3_TRY(launch_trim_hist(cfg, state, cb.distf, n, hist, pass, st));
+    SE3_TRY(launch_trim_count_eq(cfg, state, cb.distf, n, hist, block_eq, nullptr, st));
+    SE3_TRY(launch_trim_apply(cfg, state, cb.distf, n, hist, block_eq, nullptr, 0, cb.keep, st));
     return 0;
 }
 
@@ -276,7 +301,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
         }
     }
 
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) {
+    for (int i = S.begin + blockIdx.x * blockDim.x + threadIdx.x; i < S.end; i += gridDim.x * blockDim.x) {
         if (cfg.trim_active && !cb.keep[i]) continue;
         const int j = cb.idx[i];
         if (j < 0) continue;
@@ -510,15 +535,30 @@ __device__ void kabsch_rotation(const double Sg[3][3], double R[3][3]) {
         for (int c = 0; c < 3; c++) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + d * U[r][2] * V[c][2];
 }
 
+// fixed-order sum of the per-block records into one record (input of the cross-rank all-reduce)
+__global__ void __launch_bounds__(32) sum_partials_kernel(const double* __restrict__ partials, double* __restrict__ total) {
+    int lane = threadIdx.x;
+    double s = 0.0;
+    if (lane < kAcc)
+        for (int b = 0; b < kReduceBlocks; b++) s += partials[b * kReducePartials + lane];
+    total[lane] = s;
+}
+
+int launch_sum_partials(const double* partials, double* total, cudaStream_t st) {
+    sum_partials_kernel<<<1, 32, 0, st>>>(partials, total);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
 __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterState* __restrict__ st,
-                                                           const double* __restrict__ partials, double* __restrict__ history,
-                                                           unsigned int* __restrict__ hist) {
+                                                           const double* __restrict__ partials, int n_records,
+                                                           double* __restrict__ history, unsigned int* __restrict__ hist) {
     if (st->done) return;
     __shared__ double tot[kReducePartials];
     const int lane = threadIdx.x;
     if (lane < kAcc) {
         double s = 0.0;
-        for (int b = 0; b < kReduceBlocks; b++) s += partials[b * kReducePartials + lane];  // fixed order
+        for (int b = 0; b < n_records; b++) s += partials[b * kReducePartials + lane];  // fixed order
         tot[lane] = s;
     }
     if (hist)
@@ -613,9 +653,9 @@ __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterSta
     st->t_mark = global_timer_ns();
 }
 
-int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, double* history,
+int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,
                         unsigned int* hist, cudaStream_t st) {
-    solve_update_kernel<<<1, 32, 0, st>>>(cfg, state, partials, history, hist);
+    solve_update_kernel<<<1, 32, 0, st>>>(cfg, state, partials, n_records, history, hist);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }

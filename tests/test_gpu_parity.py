@@ -383,3 +383,36 @@ def test_kitti_scale_properties(ctx, orc, capi):
     Tg, sg = ctx.run(pg)
     assert np.degrees(rot_err(Tg, T_gt)) < 0.1 and np.linalg.norm(Tg[:3, 3] - T_gt[:3, 3]) < 0.05
     assert 0 < sg.num_pure_se3_iterations <= 10
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_sharded_world1_equals_plain(ctx, capi, bunny4k):
+    """se3icp_run_sharded with a one-rank NCCL communicator and the full range is the plain run"""
+    src, tgt, _ = bunny4k
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    for variant, overlap in (("pt2pl", 1.0), ("gicp", 0.7)):
+        p = capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, **dict(RRM, estimated_overlap=overlap))
+        T1, s1 = ctx.run(p)
+        ctx.comm_init(1, 0, capi.comm_unique_id())
+        T2, s2 = ctx.run_sharded(p, 0, len(src))
+        ctx.comm_destroy()
+        np.testing.assert_array_equal(T1, T2)
+        assert s1.num_iterations == s2.num_iterations
+    with pytest.raises(capi.Se3IcpError):
+        ctx.run_sharded(p, 0, len(src) // 2)  # partial range without a communicator
+
+
+def test_multi_gpu_sharded_and_batch():
+    """needs >= 2 GPUs (gpurun --gpus 2): sharded pair == single GPU, batch sharding bit-identical"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
