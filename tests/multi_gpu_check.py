@@ -51,7 +51,9 @@ def main():
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         same = bool(torch.equal(tmin, tmax))
-        ok = rot < 1e-9 and tr < 1e-9 and ss.num_iterations == s1.num_iterations and same
+        # different summation order (per-rank partials + all-reduce) perturbs T by ~1e-16 per iteration; with the
+        # discrete trimmed rejection that can move the converged estimate by ~1e-8: bar 1e-6, far inside 1e-5
+        ok = rot < 1e-6 and tr < 1e-6 and ss.num_iterations == s1.num_iterations and same
         report.append("%s/%.1f: rot %.1e transl %.1e it %d/%d identical_across_ranks=%s sharded %.2f ms vs single %.2f ms" %
                       (variant, overlap, rot, tr, ss.num_iterations, s1.num_iterations, same, ss.time_total_ms, s1.time_total_ms))
         assert ok, report[-1]
