@@ -19,6 +19,10 @@ for _ in range(3):
     T, st = ctx.run(p)
 print("pair %d/%d: %d it (%d SE3) total %.2f ms setup %.2f ms launches %d" %
       (len(src), len(tgt), st.num_iterations, st.num_pure_se3_iterations, st.time_total_ms, st.time_setup_ms, st.kernel_launches))
+pg = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, use_graph=1, **W.KITTI_PARAMS)
+for _ in range(3):
+    Tg, sg = ctx.run(pg)
+print("  with use_graph=1: total %.2f ms, identical result: %s, launches %d" % (sg.time_total_ms, bool((Tg == T).all()), sg.kernel_launches))
 for name, sid, rep in (("nn_se3", capi.STAGE_NN_SE3, 20), ("nn_xyz", capi.STAGE_NN_XYZ, 20), ("reduce", capi.STAGE_REDUCE, 20),
                        ("knn_features(target)", capi.STAGE_KNN_TARGET, 5)):
     print("  %-22s %.3f ms" % (name, ctx.time_stage(sid, rep)))

@@ -336,6 +336,13 @@ int enqueue_iteration(se3icp_ctx* c) {
     return 0;
 }
 
+void release_loop_graph(se3icp_ctx* c) {
+    if (c->loop_exec) cudaGraphExecDestroy(c->loop_exec);
+    if (c->loop_graph) cudaGraphDestroy(c->loop_graph);
+    c->loop_exec = nullptr;
+    c->loop_graph = nullptr;
+}
+
 int check_ctx(se3icp_ctx* c) {
     if (!c) {
         set_last_error("null context");
@@ -372,7 +379,7 @@ void se3icp_default_params(se3icp_params* p) {  // reference ctor .cpp:334-348
     p->scale_preprocessing = 3.0;
     p->gicp_epsilon = 1e-3;
     p->nn_mode = SE3ICP_NN_AUTO;
-    p->use_graph = 0;
+    p->use_graph = 1;  /* whole loop as one CUDA graph (conditional WHILE node) */
     p->record_history = 0;
 }
 
@@ -420,6 +427,7 @@ int se3icp_destroy(se3icp_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) se3icp_comm_destroy(c);
+    release_loop_graph(c);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -495,14 +503,47 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     SE3_CUDA(cudaEventRecord(c->ev_begin, c->stream));
     SE3_TRY(enqueue_setup(c));
     SE3_CUDA(cudaEventRecord(c->ev_setup, c->stream));
-    // Iterations: the stop/phase decision lives on the device (solve_update); the host only polls the
-    // done flag.  Every kernel early-outs once done is set, so over-issuing is harmless.
-    const long hard_cap = 1000000;
-    for (long it = 0; it < hard_cap; ++it) {
-        SE3_TRY(enqueue_iteration(c));
-        SE3_CUDA(cudaMemcpyAsync(c->h_flag, &c->dstate()->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        SE3_CUDA(cudaStreamSynchronize(c->stream));
-        if (*c->h_flag) break;
+    // Iterations: the stop/phase decision lives on the device (solve_update).
+    release_loop_graph(c);
+    c->graph_run = false;
+    const bool multi_rank = c->sharded && c->comm && c->comm_size > 1;
+    if (p->use_graph && !multi_rank) {
+        // The whole loop is ONE graph launch: a conditional WHILE node whose body is the captured iteration;
+        // its last kernel sets the condition from the device-side done flag.  The host never round-trips.
+        SE3_CUDA(cudaGraphCreate(&c->loop_graph, 0));
+        cudaGraphConditionalHandle handle;
+        SE3_CUDA(cudaGraphConditionalHandleCreate(&handle, c->loop_graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        SE3_CUDA(cudaGraphAddNode(&node, c->loop_graph, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        SE3_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        long long before = c->launches;
+        int rc = enqueue_iteration(c);
+        if (rc == 0) rc = launch_loop_condition((unsigned long long)handle, c->dstate(), c->stream);
+        cudaGraph_t captured = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &captured);
+        if (rc) return rc;
+        SE3_CUDA(ce);
+        c->launches_per_iter = c->launches - before + 1;
+        c->launches = before;
+        SE3_CUDA(cudaGraphInstantiate(&c->loop_exec, c->loop_graph, 0));
+        SE3_CUDA(cudaGraphLaunch(c->loop_exec, c->stream));
+        c->graph_run = true;
+    } else {
+        // host-driven: poll the 4-byte done flag once per iteration.  Every kernel early-outs once done
+        // is set, so over-issuing is harmless.
+        const long hard_cap = 1000000;
+        for (long it = 0; it < hard_cap; ++it) {
+            SE3_TRY(enqueue_iteration(c));
+            SE3_CUDA(cudaMemcpyAsync(c->h_flag, &c->dstate()->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            SE3_CUDA(cudaStreamSynchronize(c->stream));
+            if (*c->h_flag) break;
+        }
     }
     SE3_TRY(launch_finalize(c->cfg, c->dstate(), c->stream));
     c->launches += 1;
@@ -535,7 +576,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         stats->time_se3_correspondence_search_ms = (double)hs.t_corr_ns / 1e6;
         stats->time_before_pure_icp_ms = stats->time_total_ms;  // .cpp:957-958 measures the whole call
         stats->exact_repairs = hs.total_repairs;
-        stats->kernel_launches = c->launches;
+        stats->kernel_launches = c->launches + (c->graph_run ? c->launches_per_iter * (long long)hs.iter : 0);
     }
     return SE3ICP_OK;
 }

@@ -40,6 +40,10 @@ struct se3icp_ctx {
     se3::RunConfig cfg{};
     se3icp_params params{};
     bool run_pending = false;
+    cudaGraph_t loop_graph = nullptr;        // WHILE-loop graph of the last run (use_graph)
+    cudaGraphExec_t loop_exec = nullptr;
+    long long launches_per_iter = 0;
+    bool graph_run = false;
     bool variant_valid = true;
     long long launches = 0;
     int history_capacity = 0;

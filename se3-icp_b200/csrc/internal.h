@@ -181,6 +181,7 @@ int launch_sum_partials(const double* partials /*[kReduceBlocks][kReducePartials
                         cudaStream_t st);
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,
                         unsigned int* hist /*[4*256] trim histograms, zeroed for the next iteration*/, cudaStream_t st);
+int launch_loop_condition(unsigned long long cond_handle, const IterState* state, cudaStream_t st);
 int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st);
 int launch_init_state(IterState* state, unsigned int* hist, cudaStream_t st);
 

@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterSta
     } else {  // .cpp:724-729
         if (st->iter == cfg.max_iter || st->mse_rel < s * cfg.mse) st->done = 1;
     }
+    if (st->iter >= 1000000) st->done = 1;  // hard cap (the reference would spin forever on such parameters)
     st->total_repairs += st->repair_count;
     st->repair_count = 0;
     st->t_mark = global_timer_ns();
@@ -672,6 +673,17 @@ __global__ void finalize_kernel(RunConfig cfg, IterState* st) {
             st->T_final[4 * r + 3] = inv * st->T_total[4 * r + 3] - rc + st->c_tgt[r];
         }
     }
+}
+
+// last node of the captured iteration: tells the WHILE node of the CUDA graph whether to run the body again
+__global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const IterState* __restrict__ st) {
+    if (threadIdx.x == 0) cudaGraphSetConditional(handle, st->done ? 0u : 1u);
+}
+
+int launch_loop_condition(unsigned long long handle, const IterState* state, cudaStream_t st) {
+    loop_condition_kernel<<<1, 32, 0, st>>>((cudaGraphConditionalHandle)handle, state);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st) {

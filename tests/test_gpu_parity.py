@@ -416,3 +416,19 @@ def test_multi_gpu_sharded_and_batch():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("entry_name,variant,overlap", [("RUN_SE3_ICP", "pt2pl", 1.0), ("RUN_SE3_ICP", "gicp", 0.7),
+                                                         ("RUN_ICP", "pt2pt", 1.0), ("RUN_SE3_PURE", "pt2pl", 1.0)])
+def test_graph_loop_equals_host_loop(ctx, capi, bunny4k, entry_name, variant, overlap):
+    """use_graph=1 runs the whole iteration loop as one CUDA graph (conditional WHILE node, device-side stop
+    flag); the result must be bit-identical to the host-polled loop"""
+    src, tgt, _ = bunny4k
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    kw = dict(RRM, estimated_overlap=overlap)
+    Ta, sa = ctx.run(capi.default_params(variant=variant, entry=getattr(capi, entry_name), use_graph=0, **kw))
+    Tb, sb = ctx.run(capi.default_params(variant=variant, entry=getattr(capi, entry_name), use_graph=1, **kw))
+    np.testing.assert_array_equal(Ta, Tb)
+    assert (sa.num_iterations, sa.num_pure_se3_iterations) == (sb.num_iterations, sb.num_pure_se3_iterations)
+    assert sb.kernel_launches > 0
