@@ -81,7 +81,7 @@ typedef struct se3icp_params {
     int32_t nn_mode;                /* se3icp_nn_mode */
     int32_t use_graph;              /* 1 = capture the iteration in a CUDA graph */
     int32_t record_history;         /* 1 = keep per-iteration T_i (reference estimated_history_, hpp:63) */
-    int32_t reserved;
+    int32_t nn_coherence;           /* 1 = SE(3) search may skip queries whose previous match is provably still nearest */
 } se3icp_params;
 
 typedef struct se3icp_stats {

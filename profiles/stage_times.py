@@ -19,6 +19,11 @@ for _ in range(3):
     T, st = ctx.run(p)
 print("pair %d/%d: %d it (%d SE3) total %.2f ms setup %.2f ms launches %d" %
       (len(src), len(tgt), st.num_iterations, st.num_pure_se3_iterations, st.time_total_ms, st.time_setup_ms, st.kernel_launches))
+for coh in (0, 1):
+    pc = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, nn_coherence=coh, **W.KITTI_PARAMS)
+    for _ in range(3):
+        Tc, sc = ctx.run(pc)
+    print("  nn_coherence=%d: total %.2f ms, identical: %s" % (coh, sc.time_total_ms, bool((Tc == T).all())))
 pg = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, use_graph=1, **W.KITTI_PARAMS)
 for _ in range(3):
     Tg, sg = ctx.run(pg)

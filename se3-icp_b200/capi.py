@@ -49,7 +49,7 @@ class Params(C.Structure):
         ("nn_mode", C.c_int32),
         ("use_graph", C.c_int32),
         ("record_history", C.c_int32),
-        ("reserved", C.c_int32),
+        ("nn_coherence", C.c_int32),
     ]
 
 

@@ -111,6 +111,8 @@ CorrBuffers se3icp_ctx::corr_buffers(bool with_d2) const {
     cb.distf = corr_distf.as<float>();
     cb.keep = keep.as<uint8_t>();
     cb.repair = repair.as<int>();
+    cb.ref_q = ref_q.as<double>();
+    cb.ref_d2nd = ref_d2nd.as<double>();
     return cb;
 }
 
@@ -151,6 +153,8 @@ int fill_config(se3icp_ctx* c, const se3icp_params* p) {
     cfg.record_history = p->record_history != 0;
     long cap = std::max<long>(std::max(p->max_num_iterations, p->max_num_se3_iterations), 1);
     cfg.max_history = (int)std::min<long>(cap, 100000);
+    cfg.coherence = p->nn_coherence != 0 && cfg.has_se3;
+    cfg.coherence_thr = 0.02;  // Frobenius change of T per iteration below which second-nearest tracking pays off
     cfg.mse = p->mse;
     cfg.mse_switch = p->mse_switch_error;
     cfg.alpha = p->alpha_rot;
@@ -181,6 +185,10 @@ int alloc_run(se3icp_ctx* c) {
     SE3_TRY(c->keep.ensure(N));
     SE3_TRY(c->repair.ensure(N * sizeof(int)));
     SE3_TRY(c->d2_nd.ensure(N * sizeof(double)));
+    if (cfg.coherence) {
+        SE3_TRY(c->ref_q.ensure(N * 12 * sizeof(double)));
+        SE3_TRY(c->ref_d2nd.ensure(N * sizeof(double)));
+    }
     SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));
     SE3_TRY(c->hist.ensure(4 * 256 * sizeof(unsigned int)));
     SE3_TRY(c->block_eq.ensure((size_t)kReduceBlocks * sizeof(int)));
@@ -267,6 +275,7 @@ int enqueue_setup(se3icp_ctx* c) {
         SE3_TRY(c->se3idx.build(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.with_cf ? 1.0 : cfg.beta, ds, st,
                                 &c->launches));
     SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, (size_t)N * sizeof(int), st));
+    if (cfg.coherence) SE3_CUDA(cudaMemsetAsync(c->ref_d2nd.ptr, 0xff, (size_t)N * sizeof(double), st));  // NaN: not known
     if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
     return 0;
 }
@@ -381,6 +390,7 @@ void se3icp_default_params(se3icp_params* p) {  // reference ctor .cpp:334-348
     p->nn_mode = SE3ICP_NN_AUTO;
     p->use_graph = 1;  /* whole loop as one CUDA graph (conditional WHILE node) */
     p->record_history = 0;
+    p->nn_coherence = 1;
 }
 
 int se3icp_create(int device, void* stream, se3icp_ctx** out) {
@@ -781,6 +791,7 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
     tmp.done = 0;
     tmp.repair_count = 0;
     tmp.switch_icp = stage == SE3ICP_STAGE_NN_SE3 ? 0 : 1;
+    tmp.T_change = 1e7;  // time the full search, not the coherence shortcut
     SE3_CUDA(cudaMemcpyAsync(c->dstate(), &tmp, sizeof(IterState), cudaMemcpyHostToDevice, st));
     SourceView S = c->source_view();
     TargetView T = c->target_view();

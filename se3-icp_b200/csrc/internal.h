@@ -84,6 +84,9 @@ struct RunConfig {
     int keep_largest;
     int record_history;
     int max_history;
+    int coherence;       // SE(3) search may skip queries whose remembered match is provably still the nearest
+    int pad1;
+    double coherence_thr;  // ... once ||T_prev - T_total||_F of the last iteration is below this
     double mse;
     double mse_switch;
     double alpha;
@@ -125,6 +128,8 @@ struct CorrBuffers {
     float* distf;    // [N] stored float distance (pcl::Correspondence::distance)
     uint8_t* keep;   // [N] trim mask (valid when trim_active)
     int* repair;     // [N] queries needing the exact FP64 repair
+    double* ref_q;   // [N][12] query the remembered second-nearest distance belongs to (coherence filter)
+    double* ref_d2nd;  // [N] exact distance to the second-nearest row at that time, < 0 = not known
 };
 
 // ---- launchers (all asynchronous on `st`) ------------------------------------------------------

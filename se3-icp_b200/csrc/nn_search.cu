@@ -291,9 +291,41 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
         return (double)acc;
     };
 
-    double tau = inf;
+    // ---- temporal coherence (DESIGN.md "coherence filter") -----------------------------------------------
+    // Once the estimate moves little (T_change below cfg.coherence_thr) the search also tracks the exact
+    // SECOND-nearest distance d2nd of each query and remembers the query q_ref it was found for.  In later
+    // iterations the triangle inequality gives |q - r| >= d2nd - |q - q_ref| for every row r other than the
+    // remembered match, so if the remembered match is strictly closer than that bound it is still the unique
+    // nearest neighbour and the traversal is skipped.  Exact: a failed test just falls through to the search.
+    const bool coherent = cfg.coherence && state->T_change < cfg.coherence_thr;
+    double tau = inf;  // best squared distance
+    double b2 = inf;   // second-best squared distance (coherent mode)
     int best_id = 0x7fffffff, best_j = 0;
+    int prev = cb.idx[i];
+    const bool have_prev = prev >= 0 && prev < M;
+    if (coherent && have_prev) {
+        double dref = cb.ref_d2nd[i];
+        if (dref >= 0.0) {
+            const double* qr = cb.ref_q + (size_t)i * 12;
+            double dl = 0.0;
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                double df = q[k] - qr[k];
+                dl += df * df;
+            }
+            int j = T.inv12[prev];
+            double d1sq = exact_d2_12(q, T.rows64, m, j);
+            double d1 = sqrt(d1sq), delta = sqrt(dl);
+            if ((d1 + delta) * (1.0 + 1e-12) + 1e-300 < dref) {
+                if (lane == 0) write_se3_match(T, cfg, cb, i, q, j, d1sq);
+                return;
+            }
+        }
+    }
+
+    int skip_leaf = -1;
     auto leaf_fn = [&](int leaf) {
+        if (leaf == skip_leaf) return;
         int p = leaf * 32 + lane;
         double d2 = inf;
         int id = 0x7fffffff;
@@ -301,40 +333,78 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
             d2 = exact_d2_12(q, T.rows64, m, p);
             id = T.perm12[p];
         }
-        // warm-started searches rarely improve: only reduce across the warp when some lane beats tau
-        if (__ballot_sync(SE3_FULL, d2 < tau || (d2 == tau && id < best_id)) == 0u) return;
+        if (!coherent) {
+            // warm-started searches rarely improve: only reduce across the warp when some lane beats tau
+            if (__ballot_sync(SE3_FULL, d2 < tau || (d2 == tau && id < best_id)) == 0u) return;
+            double wd = d2;
+            int wid = id;
+            warp_argmin(wd, wid);
+            unsigned who = __ballot_sync(SE3_FULL, id == wid && d2 == wd);
+            tau = wd;
+            best_id = wid;
+            best_j = leaf * 32 + (__ffs(who) - 1);
+            return;
+        }
+        // two nearest: nothing changes unless a lane beats the second-best bound (or ties the best)
+        if (__ballot_sync(SE3_FULL, d2 < b2 || (d2 == tau && id < best_id)) == 0u) return;
         double wd = d2;
         int wid = id;
         warp_argmin(wd, wid);
         unsigned who = __ballot_sync(SE3_FULL, id == wid && d2 == wd);
-        tau = wd;
-        best_id = wid;
-        best_j = leaf * 32 + (__ffs(who) - 1);
+        int win = __ffs(who) - 1;
+        double m2 = warp_min(lane == win ? inf : d2);  // second smallest of this leaf
+        if (wid == best_id) {
+            b2 = fmin(b2, m2);  // the leaf holds the current best itself
+        } else if (wd < tau || (wd == tau && wid < best_id)) {
+            b2 = fmin(b2, fmin(tau, m2));  // old best and the leaf's runner-up compete for second place
+            tau = wd;
+            best_id = wid;
+            best_j = leaf * 32 + win;
+        } else {
+            b2 = fmin(b2, wd);
+        }
     };
 
-    int prev = cb.idx[i];
-    if (prev >= 0 && prev < M) {
+    if (have_prev && !coherent) {
         best_j = T.inv12[prev];
         best_id = prev;
         tau = exact_d2_12(q, T.rows64, m, best_j);
     } else {
-        // no warm start: the leaf around the query's own 6-D key gives the first radius
-        double Ru[9];
-        double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
+        int first;
+        if (have_prev) {
+            first = T.inv12[prev] >> 5;  // the remembered match's own leaf: best and a first runner-up
+        } else {
+            // no warm start: the leaf around the query's own 6-D key gives the first radius
+            double Ru[9];
+            double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
 #pragma unroll
-        for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
-        double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
-        uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
-        int lo = 0, hi = M;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
+            for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
+            double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
+            uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
+            int lo = 0, hi = M;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= M) lo = M - 1;
+            first = lo >> 5;
         }
-        if (lo >= M) lo = M - 1;
-        leaf_fn(lo >> 5);
+        leaf_fn(first);
+        skip_leaf = first;
     }
-    traverse_nodes(T.idx, lb_fn, tau, stacks[wib], lane, leaf_fn);
-    if (lane == 0) write_se3_match(T, cfg, cb, i, q, best_j, tau);
+    // prune against the second-best bound when it is being tracked
+    traverse_nodes(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
+    if (lane == 0) {
+        write_se3_match(T, cfg, cb, i, q, best_j, tau);
+        if (cfg.coherence) {
+            cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;
+            if (coherent) {
+                double* qr = cb.ref_q + (size_t)i * 12;
+#pragma unroll
+                for (int k = 0; k < 12; k++) qr[k] = q[k];
+            }
+        }
+    }
 }
 
 int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,

@@ -432,3 +432,25 @@ def test_graph_loop_equals_host_loop(ctx, capi, bunny4k, entry_name, variant, ov
     np.testing.assert_array_equal(Ta, Tb)
     assert (sa.num_iterations, sa.num_pure_se3_iterations) == (sb.num_iterations, sb.num_pure_se3_iterations)
     assert sb.kernel_launches > 0
+
+
+@pytest.mark.parametrize("problem", ["c1", "bunny", "kitti"])
+def test_coherence_filter_is_exact(ctx, capi, c1, bunny4k, problem):
+    """nn_coherence=1 (skip queries whose remembered match is provably still nearest) must not change a bit"""
+    if problem == "kitti":
+        src, tgt, _ = W.lidar_pair(seed=1)
+        kw = dict(W.KITTI_PARAMS)
+        variant = "gicp"
+    else:
+        src, tgt, _ = c1 if problem == "c1" else bunny4k
+        kw = dict(RRM)
+        variant = "pt2pl"
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    Ta, sa = ctx.run(capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, nn_coherence=0, **kw))
+    ia, da = ctx.correspondences()
+    Tb, sb = ctx.run(capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, nn_coherence=1, **kw))
+    ib, db = ctx.correspondences()
+    np.testing.assert_array_equal(Ta, Tb)
+    np.testing.assert_array_equal(ia, ib)
+    assert (sa.num_iterations, sa.num_pure_se3_iterations) == (sb.num_iterations, sb.num_pure_se3_iterations)
