@@ -3,6 +3,7 @@
 // the stage-level entry points used by the parity tests.  No CPU fallback anywhere: every entry
 // point fails with a status code when CUDA fails.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -154,6 +155,7 @@ int fill_config(se3icp_ctx* c, const se3icp_params* p) {
     long cap = std::max<long>(std::max(p->max_num_iterations, p->max_num_se3_iterations), 1);
     cfg.max_history = (int)std::min<long>(cap, 100000);
     cfg.coherence = p->nn_coherence != 0 && cfg.has_se3;
+    cfg.coherence_xyz = p->nn_coherence != 0 && !cfg.pure;
     cfg.coherence_thr = 0.02;  // Frobenius change of T per iteration below which second-nearest tracking pays off
     cfg.mse = p->mse;
     cfg.mse_switch = p->mse_switch_error;
@@ -185,7 +187,7 @@ int alloc_run(se3icp_ctx* c) {
     SE3_TRY(c->keep.ensure(N));
     SE3_TRY(c->repair.ensure(N * sizeof(int)));
     SE3_TRY(c->d2_nd.ensure(N * sizeof(double)));
-    if (cfg.coherence) {
+    if (cfg.coherence || cfg.coherence_xyz) {
         SE3_TRY(c->ref_q.ensure(N * 12 * sizeof(double)));
         SE3_TRY(c->ref_d2nd.ensure(N * sizeof(double)));
     }
@@ -275,7 +277,7 @@ int enqueue_setup(se3icp_ctx* c) {
         SE3_TRY(c->se3idx.build(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.with_cf ? 1.0 : cfg.beta, ds, st,
                                 &c->launches));
     SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, (size_t)N * sizeof(int), st));
-    if (cfg.coherence) SE3_CUDA(cudaMemsetAsync(c->ref_d2nd.ptr, 0xff, (size_t)N * sizeof(double), st));  // NaN: not known
+    if (cfg.coherence || cfg.coherence_xyz) SE3_CUDA(cudaMemsetAsync(c->ref_d2nd.ptr, 0xff, (size_t)N * sizeof(double), st));  // NaN: not known
     if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
     return 0;
 }
@@ -343,6 +345,22 @@ int enqueue_iteration(se3icp_ctx* c) {
         c->launches += 2;
     }
     return 0;
+}
+
+// The loop graph is the default; SE3ICP_USE_GRAPH=0/1 overrides the parameter.  Kernels inside a graph that
+// contains a conditional node cannot be profiled by Nsight Compute ("not supported for profiling"), so
+// when the process runs under ncu the host-driven loop is used and every kernel stays visible.
+bool want_graph(const se3icp_params* p) {
+    static const int forced = [] {
+        const char* e = getenv("SE3ICP_USE_GRAPH");
+        if (e && *e) return atoi(e) != 0 ? 1 : 0;
+        if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) {
+            fprintf(stderr, "[se3icp] profiler detected: using the host-driven iteration loop (graph kernels are not profilable)\n");
+            return 0;
+        }
+        return -1;
+    }();
+    return forced >= 0 ? forced != 0 : p->use_graph != 0;
 }
 
 void release_loop_graph(se3icp_ctx* c) {
@@ -517,7 +535,7 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     release_loop_graph(c);
     c->graph_run = false;
     const bool multi_rank = c->sharded && c->comm && c->comm_size > 1;
-    if (p->use_graph && !multi_rank) {
+    if (want_graph(p) && !multi_rank) {
         // The whole loop is ONE graph launch: a conditional WHILE node whose body is the captured iteration;
         // its last kernel sets the condition from the device-side done flag.  The host never round-trips.
         SE3_CUDA(cudaGraphCreate(&c->loop_graph, 0));

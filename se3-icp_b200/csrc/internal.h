@@ -62,7 +62,7 @@ struct IterState {
     int eq_budget;
     int repair_count;
     int hist_count;
-    int pad0;
+    int switch_iter;  // value of iter when the ICP phase began (-1 before)
     long long total_repairs;
     unsigned long long t_mark;      // globaltimer at the end of the previous solve/update
     unsigned long long t_corr_ns;   // accumulated correspondence-search time
@@ -85,7 +85,7 @@ struct RunConfig {
     int record_history;
     int max_history;
     int coherence;       // SE(3) search may skip queries whose remembered match is provably still the nearest
-    int pad1;
+    int coherence_xyz;   // same for the 3-D search of the ICP phase / run_icp
     double coherence_thr;  // ... once ||T_prev - T_total||_F of the last iteration is below this
     double mse;
     double mse_switch;

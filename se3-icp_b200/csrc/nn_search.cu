@@ -442,9 +442,35 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
     const double qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
     const double qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
 
-    double tau = inf;
+    // same coherence filter as the SE(3) search, in 3-D (the ICP phase moves the estimate by < 1e-3 per step)
+    const bool coherent = cfg.coherence_xyz && state->T_change < cfg.coherence_thr;
+    double tau = inf, b2 = inf;
     int best = 0x7fffffff;
+    int prev = cb.idx[i];
+    const bool have_prev = prev >= 0 && prev < I.n;
+    // the first ICP-phase iteration still sees the 12-D references of the SE(3) phase: ignore them once
+    const bool refs_are_3d = !(cfg.has_se3 && state->iter == state->switch_iter);
+    if (coherent && have_prev && refs_are_3d) {
+        double dref = cb.ref_d2nd[i];
+        if (dref >= 0.0) {
+            const double* qr = cb.ref_q + (size_t)i * 12;
+            double ex = qx - qr[0], ey = qy - qr[1], ez = qz - qr[2];
+            double d1sq = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
+            double d1 = sqrt(d1sq), delta = sqrt(ex * ex + ey * ey + ez * ez);
+            if ((d1 + delta) * (1.0 + 1e-12) + 1e-300 < dref) {
+                if (lane == 0) {
+                    cb.idx[i] = prev;
+                    cb.dist[i] = d1;
+                    cb.distf[i] = (float)d1;
+                    if (cb.d2_nd) cb.d2_nd[i] = d1sq;
+                }
+                return;
+            }
+        }
+    }
+    int skip_leaf = -1;
     auto leaf_fn = [&](int leaf) {
+        if (leaf == skip_leaf) return;
         int p = leaf * 32 + lane;
         double d2 = inf;
         int id = 0x7fffffff;
@@ -452,19 +478,38 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
             d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
             id = I.perm[p];
         }
-        if (__ballot_sync(SE3_FULL, d2 < tau || (d2 == tau && id < best)) == 0u) return;
-        warp_argmin(d2, id);
-        tau = d2;
-        best = id;
+        if (!coherent) {
+            if (__ballot_sync(SE3_FULL, d2 < tau || (d2 == tau && id < best)) == 0u) return;
+            warp_argmin(d2, id);
+            tau = d2;
+            best = id;
+            return;
+        }
+        if (__ballot_sync(SE3_FULL, d2 < b2 || (d2 == tau && id < best)) == 0u) return;
+        double wd = d2;
+        int wid = id;
+        warp_argmin(wd, wid);
+        unsigned who = __ballot_sync(SE3_FULL, id == wid && d2 == wd);
+        int win = __ffs(who) - 1;
+        double m2 = warp_min(lane == win ? inf : d2);
+        if (wid == best) {
+            b2 = fmin(b2, m2);
+        } else if (wd < tau || (wd == tau && wid < best)) {
+            b2 = fmin(b2, fmin(tau, m2));
+            tau = wd;
+            best = wid;
+        } else {
+            b2 = fmin(b2, wd);
+        }
     };
 
-    int prev = cb.idx[i];
-    if (prev >= 0 && prev < I.n) {
+    if (have_prev && !coherent) {
         tau = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
         best = prev;
     } else {
-        // no warm start: the leaf holding the query's Morton code gives the first radius
-        uint64_t key = morton63(qx, qy, qz, I.bbox);
+        // first leaf: around the remembered match (coherent mode needs a runner-up too), or, without a
+        // warm start, the leaf holding the query's Morton code
+        uint64_t key = have_prev ? morton63(I.x[prev], I.y[prev], I.z[prev], I.bbox) : morton63(qx, qy, qz, I.bbox);
         int lo = 0, hi = I.n;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
@@ -472,8 +517,9 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
         }
         if (lo >= I.n) lo = I.n - 1;
         leaf_fn(lo >> 5);
+        skip_leaf = lo >> 5;
     }
-    traverse_boxes(I, qx, qy, qz, tau, stacks[wib], lane, leaf_fn);
+    traverse_boxes(I, qx, qy, qz, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
 
     if (lane == 0) {
         double d = sqrt(tau);  // .cpp:411
@@ -481,6 +527,13 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
         cb.dist[i] = d;
         cb.distf[i] = (float)d;  // .cpp:413
         if (cb.d2_nd) cb.d2_nd[i] = tau;
+        if (cfg.coherence_xyz) {
+            cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;
+            if (coherent) {
+                double* qr = cb.ref_q + (size_t)i * 12;
+                qr[0] = qx, qr[1] = qy, qr[2] = qz;
+            }
+        }
     }
 }
 

@@ -53,6 +53,7 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->eq_budget = 0;
         st->repair_count = 0;
         st->hist_count = 0;
+        st->switch_iter = -1;
         st->total_repairs = 0;
         st->t_corr_ns = 0;
         st->t_start = global_timer_ns();
@@ -643,6 +644,7 @@ __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterSta
     } else if (!st->switch_icp) {  // .cpp:718-723
         if (st->iter == cfg.max_se3_iter || st->T_change < cfg.mse_switch) {
             st->switch_icp = 1;
+            st->switch_iter = st->iter;
             st->t_switch = global_timer_ns();
         }
     } else {  // .cpp:724-729

@@ -447,10 +447,12 @@ def test_coherence_filter_is_exact(ctx, capi, c1, bunny4k, problem):
         variant = "pt2pl"
     ctx.set_cloud(capi.SOURCE, src)
     ctx.set_cloud(capi.TARGET, tgt)
-    Ta, sa = ctx.run(capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, nn_coherence=0, **kw))
-    ia, da = ctx.correspondences()
-    Tb, sb = ctx.run(capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, nn_coherence=1, **kw))
-    ib, db = ctx.correspondences()
-    np.testing.assert_array_equal(Ta, Tb)
-    np.testing.assert_array_equal(ia, ib)
-    assert (sa.num_iterations, sa.num_pure_se3_iterations) == (sb.num_iterations, sb.num_pure_se3_iterations)
+    for entry in (capi.RUN_SE3_ICP, capi.RUN_ICP):
+        Ta, sa = ctx.run(capi.default_params(variant=variant, entry=entry, nn_coherence=0, **kw))
+        ia, da = ctx.correspondences()
+        Tb, sb = ctx.run(capi.default_params(variant=variant, entry=entry, nn_coherence=1, **kw))
+        ib, db = ctx.correspondences()
+        np.testing.assert_array_equal(Ta, Tb)
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_array_equal(da, db)
+        assert (sa.num_iterations, sa.num_pure_se3_iterations) == (sb.num_iterations, sb.num_pure_se3_iterations)
