@@ -112,6 +112,7 @@ CorrBuffers se3icp_ctx::corr_buffers(bool with_d2) const {
     cb.distf = corr_distf.as<float>();
     cb.keep = keep.as<uint8_t>();
     cb.repair = repair.as<int>();
+    cb.work = work.as<int>();
     cb.ref_q = ref_q.as<double>();
     cb.ref_d2nd = ref_d2nd.as<double>();
     return cb;
@@ -190,6 +191,7 @@ int alloc_run(se3icp_ctx* c) {
     if (cfg.coherence || cfg.coherence_xyz) {
         SE3_TRY(c->ref_q.ensure(N * 12 * sizeof(double)));
         SE3_TRY(c->ref_d2nd.ensure(N * sizeof(double)));
+        SE3_TRY(c->work.ensure(N * sizeof(int)));
     }
     SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));
     SE3_TRY(c->hist.ensure(4 * 256 * sizeof(unsigned int)));
@@ -289,6 +291,8 @@ int enqueue_iteration(se3icp_ctx* c) {
     TargetView T = c->target_view();
     CorrBuffers cb = c->corr_buffers(false);
     IterState* ds = c->dstate();
+    SE3_TRY(launch_nn_filter(S, T, cfg, ds, cb, st));
+    if (cfg.coherence || cfg.coherence_xyz) c->launches += 1;
     if (cfg.has_se3) {
         int mode = c->params.nn_mode;
         if (mode == SE3ICP_NN_BRUTE_F32 || mode == SE3ICP_NN_EXACT_F64) {

@@ -63,6 +63,8 @@ struct IterState {
     int repair_count;
     int hist_count;
     int switch_iter;  // value of iter when the ICP phase began (-1 before)
+    int work_count;   // entries of the coherence work list (reset every iteration)
+    int pad2;
     long long total_repairs;
     unsigned long long t_mark;      // globaltimer at the end of the previous solve/update
     unsigned long long t_corr_ns;   // accumulated correspondence-search time
@@ -128,7 +130,8 @@ struct CorrBuffers {
     float* distf;    // [N] stored float distance (pcl::Correspondence::distance)
     uint8_t* keep;   // [N] trim mask (valid when trim_active)
     int* repair;     // [N] queries needing the exact FP64 repair
-    double* ref_q;   // [N][12] query the remembered second-nearest distance belongs to (coherence filter)
+    int* work;       // [N] queries the coherence filter could not settle this iteration
+    double* ref_q;   // [12][N] query the remembered second-nearest distance belongs to (coherence filter)
     double* ref_d2nd;  // [N] exact distance to the second-nearest row at that time, < 0 = not known
 };
 
@@ -162,6 +165,8 @@ int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t
 int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, double* cov /*[6][n]*/, cudaStream_t st);
 
 // nn_search.cu
+int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                     cudaStream_t st);
 int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                        cudaStream_t st);
 int launch_nn_se3_brute(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,

@@ -250,6 +250,70 @@ int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConf
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coherence filter, one THREAD per query (coalesced plane loads): settles every query whose remembered
+// match is provably still its unique nearest neighbour and appends the others to the work list that the
+// warp-per-query search kernels consume.  Runs before both searches; a no-op in non-coherent iterations.
+__global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                         IterState* __restrict__ state, CorrBuffers cb) {
+    if (state->done) return;
+    const bool se3 = se3_phase_active(cfg, state);
+    const bool enabled = se3 ? cfg.coherence : cfg.coherence_xyz;
+    if (!enabled || !(state->T_change < cfg.coherence_thr)) return;
+    const int i = S.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.end) return;
+    const double* Tm = state->T_total;
+    const size_t n = (size_t)S.n, m = (size_t)T.n;
+    bool settled = false;
+    const int prev = cb.idx[i];
+    const double dref = cb.ref_d2nd[i];
+    // the first ICP-phase iteration still sees the 12-D references of the SE(3) phase: ignore them once
+    const bool refs_match_space = se3 || !(cfg.has_se3 && state->iter == state->switch_iter);
+    if (prev >= 0 && prev < T.n && dref >= 0.0 && refs_match_space) {
+        if (se3) {
+            double q[12];
+            make_query(S, cfg, Tm, i, q);
+            double dl = 0.0;
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                double df = q[k] - cb.ref_q[k * n + i];
+                dl += df * df;
+            }
+            int j = T.inv12[prev];
+            double d1sq = exact_d2_12(q, T.rows64, m, j);
+            if ((sqrt(d1sq) + sqrt(dl)) * (1.0 + 1e-12) + 1e-300 < dref) {
+                write_se3_match(T, cfg, cb, i, q, j, d1sq);
+                settled = true;
+            }
+        } else {
+            const double px = S.x[i], py = S.y[i], pz = S.z[i];
+            const double qx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3];
+            const double qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
+            const double qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
+            double ex = qx - cb.ref_q[i], ey = qy - cb.ref_q[n + i], ez = qz - cb.ref_q[2 * n + i];
+            double d1sq = sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]);
+            double d1 = sqrt(d1sq);
+            if ((d1 + sqrt(ex * ex + ey * ey + ez * ez)) * (1.0 + 1e-12) + 1e-300 < dref) {
+                cb.dist[i] = d1;
+                cb.distf[i] = (float)d1;
+                if (cb.d2_nd) cb.d2_nd[i] = d1sq;
+                settled = true;
+            }
+        }
+    }
+    if (!settled) cb.work[atomicAdd(&state->work_count, 1)] = i;
+}
+
+int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                     cudaStream_t st) {
+    if (!cfg.coherence && !cfg.coherence_xyz) return 0;
+    int g = (S.end - S.begin + 255) / 256;
+    if (g < 1) g = 1;
+    nn_filter_kernel<<<g, 256, 0, st>>>(S, T, cfg, state, cb);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 constexpr int kTreeWarps = 8;
 
 __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
@@ -260,8 +324,17 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = S.begin + blockIdx.x * kTreeWarps + wib;
-    if (i >= S.end) return;
+    // coherent iterations only search the queries the filter kernel could not settle (cb.work list)
+    const bool coherent = cfg.coherence && state->T_change < cfg.coherence_thr;
+    const int w = blockIdx.x * kTreeWarps + wib;
+    int i;
+    if (coherent) {
+        if (w >= state->work_count) return;
+        i = cb.work[w];
+    } else {
+        i = S.begin + w;
+        if (i >= S.end) return;
+    }
     const int M = T.n;
     const size_t m = (size_t)M, tn = (size_t)T.idx.total_nodes;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -297,31 +370,11 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
     // iterations the triangle inequality gives |q - r| >= d2nd - |q - q_ref| for every row r other than the
     // remembered match, so if the remembered match is strictly closer than that bound it is still the unique
     // nearest neighbour and the traversal is skipped.  Exact: a failed test just falls through to the search.
-    const bool coherent = cfg.coherence && state->T_change < cfg.coherence_thr;
     double tau = inf;  // best squared distance
     double b2 = inf;   // second-best squared distance (coherent mode)
     int best_id = 0x7fffffff, best_j = 0;
     int prev = cb.idx[i];
     const bool have_prev = prev >= 0 && prev < M;
-    if (coherent && have_prev) {
-        double dref = cb.ref_d2nd[i];
-        if (dref >= 0.0) {
-            const double* qr = cb.ref_q + (size_t)i * 12;
-            double dl = 0.0;
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                double df = q[k] - qr[k];
-                dl += df * df;
-            }
-            int j = T.inv12[prev];
-            double d1sq = exact_d2_12(q, T.rows64, m, j);
-            double d1 = sqrt(d1sq), delta = sqrt(dl);
-            if ((d1 + delta) * (1.0 + 1e-12) + 1e-300 < dref) {
-                if (lane == 0) write_se3_match(T, cfg, cb, i, q, j, d1sq);
-                return;
-            }
-        }
-    }
 
     int skip_leaf = -1;
     auto leaf_fn = [&](int leaf) {
@@ -399,9 +452,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
         if (cfg.coherence) {
             cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;
             if (coherent) {
-                double* qr = cb.ref_q + (size_t)i * 12;
+                double* qr = cb.ref_q + i;
 #pragma unroll
-                for (int k = 0; k < 12; k++) qr[k] = q[k];
+                for (int k = 0; k < 12; k++) qr[(size_t)k * S.n] = q[k];
             }
         }
     }
@@ -431,8 +484,16 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = S.begin + blockIdx.x * kXyzWarps + wib;
-    if (i >= S.end) return;
+    const bool coherent = cfg.coherence_xyz && state->T_change < cfg.coherence_thr;
+    const int w = blockIdx.x * kXyzWarps + wib;
+    int i;
+    if (coherent) {
+        if (w >= state->work_count) return;
+        i = cb.work[w];
+    } else {
+        i = S.begin + w;
+        if (i >= S.end) return;
+    }
     const CloudIndex& I = T.idx;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
@@ -442,32 +503,10 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
     const double qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
     const double qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
 
-    // same coherence filter as the SE(3) search, in 3-D (the ICP phase moves the estimate by < 1e-3 per step)
-    const bool coherent = cfg.coherence_xyz && state->T_change < cfg.coherence_thr;
     double tau = inf, b2 = inf;
     int best = 0x7fffffff;
     int prev = cb.idx[i];
     const bool have_prev = prev >= 0 && prev < I.n;
-    // the first ICP-phase iteration still sees the 12-D references of the SE(3) phase: ignore them once
-    const bool refs_are_3d = !(cfg.has_se3 && state->iter == state->switch_iter);
-    if (coherent && have_prev && refs_are_3d) {
-        double dref = cb.ref_d2nd[i];
-        if (dref >= 0.0) {
-            const double* qr = cb.ref_q + (size_t)i * 12;
-            double ex = qx - qr[0], ey = qy - qr[1], ez = qz - qr[2];
-            double d1sq = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
-            double d1 = sqrt(d1sq), delta = sqrt(ex * ex + ey * ey + ez * ez);
-            if ((d1 + delta) * (1.0 + 1e-12) + 1e-300 < dref) {
-                if (lane == 0) {
-                    cb.idx[i] = prev;
-                    cb.dist[i] = d1;
-                    cb.distf[i] = (float)d1;
-                    if (cb.d2_nd) cb.d2_nd[i] = d1sq;
-                }
-                return;
-            }
-        }
-    }
     int skip_leaf = -1;
     auto leaf_fn = [&](int leaf) {
         if (leaf == skip_leaf) return;
@@ -503,13 +542,16 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
         }
     };
 
-    if (have_prev && !coherent) {
+    // warm start: the previous match (a single candidate) ...
+    if (have_prev) {
         tau = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
         best = prev;
-    } else {
-        // first leaf: around the remembered match (coherent mode needs a runner-up too), or, without a
-        // warm start, the leaf holding the query's Morton code
-        uint64_t key = have_prev ? morton63(I.x[prev], I.y[prev], I.z[prev], I.bbox) : morton63(qx, qy, qz, I.bbox);
+    }
+    // ... plus, whenever a runner-up is needed or the previous match may be far (cold start, first iteration
+    // after the SE(3) phase), the leaf holding the query's own Morton code
+    const bool after_switch = cfg.has_se3 && state->iter == state->switch_iter;
+    if (coherent || !have_prev || after_switch) {
+        uint64_t key = morton63(qx, qy, qz, I.bbox);
         int lo = 0, hi = I.n;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
@@ -530,8 +572,8 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
         if (cfg.coherence_xyz) {
             cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;
             if (coherent) {
-                double* qr = cb.ref_q + (size_t)i * 12;
-                qr[0] = qx, qr[1] = qy, qr[2] = qz;
+                double* qr = cb.ref_q + i;
+                qr[0] = qx, qr[(size_t)S.n] = qy, qr[2 * (size_t)S.n] = qz;
             }
         }
     }

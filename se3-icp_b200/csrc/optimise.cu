@@ -54,6 +54,7 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->repair_count = 0;
         st->hist_count = 0;
         st->switch_iter = -1;
+        st->work_count = 0;
         st->total_repairs = 0;
         st->t_corr_ns = 0;
         st->t_start = global_timer_ns();
@@ -653,6 +654,7 @@ __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterSta
     if (st->iter >= 1000000) st->done = 1;  // hard cap (the reference would spin forever on such parameters)
     st->total_repairs += st->repair_count;
     st->repair_count = 0;
+    st->work_count = 0;
     st->t_mark = global_timer_ns();
 }
 
