@@ -14,11 +14,11 @@
 namespace se3 {
 
 constexpr int kKnnWarps = 8;
-constexpr int kPend = 64;  // pending-candidate buffer per warp (merged into the list 32 at a time)
+constexpr int kPool = 256;  // unsorted candidate pool per warp
 
 struct KnnScratch {
-    unsigned long long d[kPend];
-    int id[kPend];
+    unsigned long long d[kPool];
+    int id[kPool];
     int2 stack[kStackEntries];
 };
 
@@ -28,7 +28,11 @@ struct KnnScratch {
 typedef unsigned long long key_t;
 constexpr key_t kInfKey = 0x7ff0000000000000ULL;
 
-__device__ __forceinline__ bool key_less(key_t da, int ia, key_t db, int ib) { return da < db || (da == db && ia < ib); }
+// distances are non-negative and never NaN, so the FP64 compare (idle FP64 pipe) orders like the bit pattern
+__device__ __forceinline__ bool key_less(key_t da, int ia, key_t db, int ib) {
+    double xa = __longlong_as_double((long long)da), xb = __longlong_as_double((long long)db);
+    return xa < xb || (xa == xb && ia < ib);
+}
 
 __device__ __forceinline__ void ce_lane(key_t& dl, int& il, key_t& dh, int& ih) {  // in-lane: low slot gets the min
     if (key_less(dh, ih, dl, il)) {
@@ -91,7 +95,7 @@ __device__ __forceinline__ void list_at(const key_t (&Ld)[4], const int (&Li)[4]
     i = __shfl_sync(SE3_FULL, si, e & 31);
 }
 
-__global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex I, FeatureArgs fa) {
+__global__ void __launch_bounds__(kKnnWarps * 32, 3) knn_features_kernel(CloudIndex I, FeatureArgs fa) {
     __shared__ KnnScratch scratch[kKnnWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // query = Morton position s.  Warps past the end redo the last query without writing, so the whole
@@ -110,51 +114,84 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     const int K = fa.K < I.n ? fa.K : I.n;
     key_t Ld[4] = {kInfKey, kInfKey, kInfKey, kInfKey};
     int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-    int pend = 0;           // candidates waiting in W.d / W.id
-    key_t tau_bits = kInfKey;
-    int tau_id = 0x7fffffff;
-    double tau = __longlong_as_double((long long)kInfKey);
     const int n_leaves = I.level_cnt[0];
+    const double inf = __longlong_as_double((long long)kInfKey);
 
-    auto refresh_tau = [&]() {
-        list_at(Ld, Li, K - 1, tau_bits, tau_id);
-        tau = __longlong_as_double((long long)tau_bits);
-    };
-    // merge 32 pending candidates (the last 32 of the buffer) into the list
-    auto flush32 = [&]() {
-        int take = pend < 32 ? pend : 32;
-        int src = pend - take + lane;
-        key_t cd = kInfKey;
-        int ci = 0x7fffffff;
-        if (lane < take) {
-            cd = W.d[src];
-            ci = W.id[src];
+    // Search phase: candidates within the current radius go to an UNSORTED pool in shared memory.  When the
+    // pool fills up, a bisection on the distance value (8 compares + ballots per step, no data movement)
+    // finds a radius that keeps between K and K+24 of them and the pool is compacted.  Sorting happens
+    // once, at the end, on the ~K survivors.
+    int pool = 0;
+    double tau = inf;
+    auto shrink_pool = [&]() {
+        if (pool <= K + 24) return;
+        double e[8];
+        int eid[8];
+        double lo = inf, hi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int t = lane + 32 * k;
+            e[k] = inf;
+            eid[k] = 0;
+            if (t < pool) {
+                e[k] = __longlong_as_double((long long)W.d[t]);
+                eid[k] = W.id[t];
+                lo = fmin(lo, e[k]);
+                hi = fmax(hi, e[k]);
+            }
+        }
+        lo = warp_min(lo);
+        hi = warp_max(hi);  // count(d <= hi) = pool >= K always holds for hi
+        for (int it = 0; it < 14; it++) {
+            double mid = 0.5 * (lo + hi);
+            if (!(mid > lo && mid < hi)) break;
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) c += __popc(__ballot_sync(SE3_FULL, e[k] <= mid));
+            if (c < K) {
+                lo = mid;
+            } else {
+                hi = mid;
+                if (c <= K + 24) break;
+            }
         }
         __syncwarp();
-        pend -= take;
-        merge32(Ld, Li, cd, ci, lane);
-        refresh_tau();
+        int out = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            bool keep = e[k] <= hi;  // padding is +inf and hi is finite
+            unsigned m = __ballot_sync(SE3_FULL, keep);
+            if (keep) {
+                int pos = out + __popc(m & ((1u << lane) - 1u));
+                W.d[pos] = (key_t)__double_as_longlong(e[k]);
+                W.id[pos] = eid[k];
+            }
+            out += __popc(m);
+        }
+        pool = out;
+        tau = hi;
+        __syncwarp();
     };
     auto eval_leaf = [&](int leaf) {
         int p = leaf * 32 + lane;
         bool pass = false;
-        key_t db = kInfKey;
+        double d2 = inf;
         int id = 0x7fffffff;
         if (p < I.n) {
-            db = (key_t)__double_as_longlong(sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]));
+            d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
             id = I.perm[p];
-            pass = key_less(db, id, tau_bits, tau_id);
+            pass = d2 <= tau;
         }
         unsigned m = __ballot_sync(SE3_FULL, pass);
         if (m == 0u) return;
         if (pass) {
-            int pos = pend + __popc(m & ((1u << lane) - 1u));
-            W.d[pos] = db;
+            int pos = pool + __popc(m & ((1u << lane) - 1u));
+            W.d[pos] = (key_t)__double_as_longlong(d2);
             W.id[pos] = id;
         }
-        pend += __popc(m);
+        pool += __popc(m);
         __syncwarp();
-        if (pend >= 32) flush32();
+        if (pool > kPool - 32) shrink_pool();
     };
 
     // seed: the leaves around the query in Morton order give a near-final search radius
@@ -164,12 +201,23 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_features_kernel(CloudIndex
     const int w1 = L + half < n_leaves - 1 ? L + half : n_leaves - 1;
     if (active) {
         for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
-        while (pend > 0) flush32();
+        shrink_pool();
         traverse_boxes(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
             if (leaf >= w0 && leaf <= w1) return;
             eval_leaf(leaf);
         });
-        while (pend > 0) flush32();
+        shrink_pool();
+        // exact order of the survivors: merge them, 32 at a time, into the register-resident sorted list
+        for (int base = 0; base < pool; base += 32) {
+            int t = base + lane;
+            key_t cd = kInfKey;
+            int ci = 0x7fffffff;
+            if (t < pool) {
+                cd = W.d[t];
+                ci = W.id[t];
+            }
+            merge32(Ld, Li, cd, ci, lane);
+        }
     }
     const int cnt = K;  // the list now holds the min(K, n) nearest, ascending, then padding
 

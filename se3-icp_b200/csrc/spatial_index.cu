@@ -43,25 +43,39 @@ __global__ void __launch_bounds__(256) sum_xyz_kernel(const double* __restrict__
     }
 }
 
-__device__ __forceinline__ void center_from_partials(const double* __restrict__ partial, int n, double c[3]) {
+// Block-cooperative (256 threads), fixed-order reduction of the per-block partial sums -> centre.
+// Must be called by all threads of the block; c lives in shared memory.
+__device__ __forceinline__ void center_from_partials(const double* __restrict__ partial, int n, double* c, double (*scratch)[8]) {
     double s0 = 0, s1 = 0, s2 = 0;
-    for (int b = 0; b < kReduceBlocks; b++) {
+    for (int b = threadIdx.x; b < kReduceBlocks; b += blockDim.x) {
         s0 += partial[3 * b];
         s1 += partial[3 * b + 1];
         s2 += partial[3 * b + 2];
     }
-    double inv = 1.0 / (double)n;
-    c[0] = s0 * inv;
-    c[1] = s1 * inv;
-    c[2] = s2 * inv;
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        scratch[0][w] = s0;
+        scratch[1][w] = s1;
+        scratch[2][w] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int k = 0; k < 8; k++) t += scratch[threadIdx.x][k];
+        c[threadIdx.x] = t * (1.0 / (double)n);
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) maxdist_kernel(const double* __restrict__ aos, int n, const double* __restrict__ psum,
                                                        double* __restrict__ pmax) {
     __shared__ double c[3];
     __shared__ double sm[8];
-    if (threadIdx.x == 0) center_from_partials(psum, n, c);
-    __syncthreads();
+    __shared__ double scratch[3][8];
+    center_from_partials(psum, n, c, scratch);
     double best = -1.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double dx = aos[3 * (size_t)i] - c[0], dy = aos[3 * (size_t)i + 1] - c[1], dz = aos[3 * (size_t)i + 2] - c[2];
@@ -84,10 +98,16 @@ __global__ void __launch_bounds__(256) normalise_kernel(const double* __restrict
                                                          double* __restrict__ x, double* __restrict__ y, double* __restrict__ z) {
     __shared__ double c[3];
     __shared__ double s_scale;
+    __shared__ double scratch[3][8];
+    center_from_partials(psum_self, n, c, scratch);
+    double rmax = -1.0;
+    for (int b = threadIdx.x; b < kReduceBlocks; b += blockDim.x) rmax = fmax(rmax, fmax(pmax_src[b], pmax_tgt[b]));
+    rmax = warp_max(rmax);
+    if ((threadIdx.x & 31) == 0) scratch[0][threadIdx.x >> 5] = rmax;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        center_from_partials(psum_self, n, c);
-        double r = -1.0;
-        for (int b = 0; b < kReduceBlocks; b++) r = fmax(r, fmax(pmax_src[b], pmax_tgt[b]));
+        double r = scratch[0][0];
+        for (int k = 1; k < 8; k++) r = fmax(r, scratch[0][k]);
         s_scale = scale_pre * (1.0 / r);
         if (blockIdx.x == 0) {
             double* dst = which == SE3ICP_SOURCE ? state->c_src : state->c_tgt;
@@ -193,13 +213,14 @@ __global__ void __launch_bounds__(256) bbox_partial_kernel(const double* __restr
     }
 }
 
+// 6 warps, warp d reduces component d of the per-block boxes
 __global__ void bbox_final_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ bbox) {
-    int t = threadIdx.x;
-    if (t < 6) {
-        double r = part[t];
-        for (int b = 1; b < nblocks; b++) r = t < 3 ? fmin(r, part[b * 6 + t]) : fmax(r, part[b * 6 + t]);
-        bbox[t] = r;
-    }
+    int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d >= 6) return;
+    double r = d < 3 ? 1e300 : -1e300;
+    for (int b = lane; b < nblocks; b += 32) r = d < 3 ? fmin(r, part[b * 6 + d]) : fmax(r, part[b * 6 + d]);
+    r = d < 3 ? warp_min(r) : warp_max(r);
+    if (lane == 0) bbox[d] = r;
 }
 
 __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ x, const double* __restrict__ y,
@@ -327,7 +348,7 @@ int IndexStorage::build(cudaStream_t st, long long* launches) {
     int g = grid_for(n, 256, 148 * 8);
     bbox_partial_kernel<<<kReduceBlocks, 256, 0, st>>>(x.as<double>(), y.as<double>(), z.as<double>(), n,
                                                         bbox_part.as<double>());
-    bbox_final_kernel<<<1, 32, 0, st>>>(bbox_part.as<double>(), kReduceBlocks, bbox.as<double>());
+    bbox_final_kernel<<<1, 192, 0, st>>>(bbox_part.as<double>(), kReduceBlocks, bbox.as<double>());
     morton_kernel<<<g, 256, 0, st>>>(x.as<double>(), y.as<double>(), z.as<double>(), n, bbox.as<double>(),
                                       keys_tmp.as<uint64_t>(), vals_tmp.as<int>());
     SE3_CUDA(cudaGetLastError());
