@@ -274,7 +274,11 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "accuracy": {"max_rot_err_rad_vs_gt": max(e[0] for e in errs), "max_transl_err_m_vs_gt": max(e[1] for e in errs)},
+            # benchmark_synthetic.cpp:410 success criterion (2 deg, 0.25); the method itself does not converge on
+            # every synthetic scene (straight corridors) and the CPU oracle returns the same transforms
+            "accuracy": {"max_rot_err_rad_vs_gt": max(e[0] for e in errs), "max_transl_err_m_vs_gt": max(e[1] for e in errs),
+                         "pairs_within_2deg_0.25m": int(sum(1 for e in errs if np.degrees(e[0]) <= 2.0 and e[1] <= 0.25)),
+                         "pairs": P},
             "contexts_per_gpu": args.contexts,
         }
     for c in ctxs:

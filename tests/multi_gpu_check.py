@@ -58,6 +58,22 @@ def main():
                       (variant, overlap, rot, tr, ss.num_iterations, s1.num_iterations, same, ss.time_total_ms, s1.time_total_ms))
         assert ok, report[-1]
 
+    # one large pair (configs[4] style, 1 M points here): sharded vs whole, se3_pt2pl, overlap 1.0
+    big_s, big_t, big_T = W.lidar_pair(seed=3, n_az=16000)
+    p = capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, estimated_overlap=1.0, **RRM)
+    ctx.set_cloud(capi.SOURCE, big_s)
+    ctx.set_cloud(capi.TARGET, big_t)
+    T1, s1 = ctx.run(p)
+    T1, s1 = ctx.run(p)
+    b, e = sh.shard_range(len(big_s), world, rank)
+    Ts, ss = ctx.run_sharded(p, b, e)
+    Ts, ss = ctx.run_sharded(p, b, e)
+    rot, tr = W.rotation_error(Ts, T1), float(np.linalg.norm(Ts[:3, 3] - T1[:3, 3]))
+    report.append("large pair %d/%d points: rot %.1e transl %.1e it %d/%d; sharded %.1f ms vs single GPU %.1f ms; vs GT rot %.1e transl %.3f" %
+                  (len(big_s), len(big_t), rot, tr, ss.num_iterations, s1.num_iterations, ss.time_total_ms, s1.time_total_ms,
+                   W.rotation_error(Ts, big_T), float(np.linalg.norm(Ts[:3, 3] - big_T[:3, 3]))))
+    assert rot < 1e-6 and tr < 1e-6 and ss.num_iterations == s1.num_iterations, report[-1]
+
     # batch mode: 6 pairs round robin
     pairs = [W.bunny_problem("easy", seed=10 + i, n_points=4167) for i in range(6)]
     p = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, estimated_overlap=1.0, **RRM)

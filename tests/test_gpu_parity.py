@@ -4,6 +4,8 @@ against the CPU oracle on identical inputs.
 Bars (BASELINE.json north_star): correspondence / neighbour indices bit-exact except equal-distance
 ties within 1e-6 relative; LRFs and normals within 1e-4 (normals up to sign); final transforms within
 1e-5 rad and 1e-5 x cloud extent."""
+import os
+
 import numpy as np
 import pytest
 
@@ -383,6 +385,31 @@ def test_kitti_scale_properties(ctx, orc, capi):
     Tg, sg = ctx.run(pg)
     assert np.degrees(rot_err(Tg, T_gt)) < 0.1 and np.linalg.norm(Tg[:3, 3] - T_gt[:3, 3]) < 0.05
     assert 0 < sg.num_pure_se3_iterations <= 10
+    gold = np.load(os.path.join(W.GOLDEN, "fullsize_oracle.npz"))  # oracle at full size (make_golden_fullsize.py)
+    assert list(gold["kitti_n"]) == [len(src), len(tgt)]
+    assert_transform_parity(Tg, gold["kitti_T"], tgt)
+    assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold["kitti_it"])
+
+
+def test_lounge_scale_with_cf(ctx, orc, capi):
+    """BASELINE.json configs[3]: lounge-like RGB-D pair, se3_gicp_with_cf (benchmark_lounge.cpp:183-186).
+    Parity against the oracle on the stride-4 image (15 k points); at full resolution (~250 k points) the
+    registration must recover the synthetic ground truth and report the reference's timing fields."""
+    src, tgt, T_gt = W.rgbd_pair(seed=0, stride=4)
+    Tg, sg, To, so = run_both(ctx, orc, capi, src, tgt, "RUN_SE3_ICP_CF", "gicp", **W.LOUNGE_PARAMS)
+    assert_transform_parity(Tg, To, tgt)
+    assert (sg.num_iterations, sg.num_pure_se3_iterations) == (so.num_iterations, so.num_pure_se3_iterations)
+    src, tgt, T_gt = W.rgbd_pair(seed=0)
+    assert len(src) > 200_000
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    Tg, sg = ctx.run(capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP_CF, **W.LOUNGE_PARAMS))
+    gold = np.load(os.path.join(W.GOLDEN, "fullsize_oracle.npz"))  # oracle at full size (make_golden_fullsize.py)
+    assert list(gold["lounge_n"]) == [len(src), len(tgt)]
+    assert_transform_parity(Tg, gold["lounge_T"], tgt)
+    assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold["lounge_it"])
+    assert np.degrees(rot_err(Tg, T_gt)) < 1.0 and np.linalg.norm(Tg[:3, 3] - T_gt[:3, 3]) < 0.15  # what the method reaches here
+    assert sg.time_se3_correspondence_search_ms > 0 and sg.time_before_pure_icp_ms >= sg.time_se3_correspondence_search_ms
 
 
 # ---------------------------------------------------------------------------------------------------
