@@ -35,6 +35,7 @@ import workloads as W  # noqa: E402
 METRIC = "SE(3)-ICP registrations/s @KITTI-size clouds (se3_gicp)"
 UNIT = "registrations/s"
 UNIQUE_PAIRS = 8  # distinct synthetic scenes per GPU, cycled to pairs_per_gpu
+NCU_TRAFFIC_BYTES = 25224704  # see roofline.traffic below
 
 
 def parse():
@@ -74,7 +75,7 @@ def config_dict(args, pairs, n_gpus):
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -96,26 +97,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """summary over the samples taken inside [t_begin, t_end] (wall clock); all samples if none fall inside"""
+        import datetime
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        used = inside if inside else rows
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        reasons = set()
+        for r in used:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in used])), "sm_max_mhz": float(np.max([r[2] for r in used])),
+                "reasons": sorted(reasons), "samples": len(used), "window": "timed region" if inside else "warm-up + timed region"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -208,13 +215,15 @@ def run_b200(args):
     step_dev = lambda: capi.run_batch(ctxs, dev_list, params, device_inputs=True)  # noqa: E731
     step_host = lambda: capi.run_batch(ctxs, pin_list, params, device_inputs=False)  # noqa: E731
 
-    for _ in range(args.warmup):
-        step_dev()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_dev()
+    t_begin = time.time()
     ms, out = timed(step_dev, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     T_dev, stats = out
     launches = int(sum(s.kernel_launches for s in stats)) * args.steps
     value = world * P * args.steps / (ms / 1e3)
@@ -231,17 +240,33 @@ def run_b200(args):
 
     result = None
     if rank == 0:
-        # roofline of the dominant kernel, measured live on the stream it runs on
+        # roofline of the dominant stage (SE(3) correspondence search = nn_filter_kernel + nn_se3_tree_kernel),
+        # measured live over the timed region: the library time-stamps the stage on the device (globaltimer at
+        # the end of the previous solve and at the start of the first kernel after the search), summed over the
+        # SE(3) iterations of every pair of the last timed step.
+        # (Taken on one context running the unique pairs back to back: with several contexts sharing the GPU the
+        # stamps of one stream would include the other streams' kernels.)
+        se3_ms, se3_launches = 0.0, 0
+        for k in range(UNIQUE_PAIRS):
+            ctxs[0].set_cloud_device(capi.SOURCE, dev[k][0].data_ptr(), dev[k][0].shape[0])
+            ctxs[0].set_cloud_device(capi.TARGET, dev[k][1].data_ptr(), dev[k][1].shape[0])
+            _, sk = ctxs[0].run(params)
+            se3_ms += sk.time_se3_phase_search_ms
+            se3_launches += sk.num_pure_se3_iterations
+        ms_nn = se3_ms / max(se3_launches, 1)
+        n = int(np.mean([len(pairs[i][0]) for i in order]))
+        m = int(np.mean([len(pairs[i][1]) for i in order]))
+        alg_bytes = 48 * n + 48 * m + 8 * n
+        # isolated re-launches of single kernels on one pair (CUDA events on the context's stream)
         c0 = ctxs[0]
         s0, t0, _ = pairs[0]
         c0.set_cloud_device(capi.SOURCE, dev[0][0].data_ptr(), len(s0))
         c0.set_cloud_device(capi.TARGET, dev[0][1].data_ptr(), len(t0))
         _, st0 = c0.run(params)
-        ms_nn = c0.time_stage(capi.STAGE_NN_SE3, 10)
-        stage_ms = {"nn_se3_sweep": ms_nn, "nn_xyz": c0.time_stage(capi.STAGE_NN_XYZ, 10),
-                    "reduce_gicp": c0.time_stage(capi.STAGE_REDUCE, 10), "knn_features_target": c0.time_stage(capi.STAGE_KNN_TARGET, 3)}
-        n, m = len(s0), len(t0)
-        alg_bytes = 48 * n + 48 * m + 8 * n
+        stage_ms = {"nn_se3_full_search_all_queries": c0.time_stage(capi.STAGE_NN_SE3, 10),
+                    "nn_xyz_full_search_all_queries": c0.time_stage(capi.STAGE_NN_XYZ, 10),
+                    "reduce_gicp": c0.time_stage(capi.STAGE_REDUCE, 10),
+                    "knn_features_target": c0.time_stage(capi.STAGE_KNN_TARGET, 3)}
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
@@ -249,9 +274,14 @@ def run_b200(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (ms_nn * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "nn_se3_brute_kernel", "algorithmic_bytes": alg_bytes,
-                    "kernel_ms": ms_nn, "peak_source": peak_src,
-                    "queries_per_s": n / (ms_nn * 1e-3), "pairs_per_s": n * m / (ms_nn * 1e-3),
+                    # dram__bytes_read.sum + dram__bytes_write.sum of nn_se3_tree_kernel, first (cold) launch of a pair,
+                    # ncu --set full capture summarised in profiles/r1_summary_v1.md
+                    "traffic": NCU_TRAFFIC_BYTES,
+                    "kernel": "SE(3) correspondence stage: nn_filter_kernel + nn_se3_tree_kernel",
+                    "algorithmic_bytes": alg_bytes, "kernel_ms": ms_nn, "launches_averaged": se3_launches,
+                    "peak_source": peak_src, "queries_per_s": n / (ms_nn * 1e-3),
+                    "note": "exact 12-D search over L2-resident clouds: pointer-chasing, ~0 DRAM traffic by design; "
+                            "HBM fraction is reported as required but the limiter is load latency (see DESIGN.md)",
                     "iterations": st0.num_iterations, "se3_iterations": st0.num_pure_se3_iterations,
                     "single_pair_ms": st0.time_total_ms, "single_pair_setup_ms": st0.time_setup_ms,
                     "stage_ms": stage_ms}
@@ -259,14 +289,14 @@ def run_b200(args):
         orc = graft.load_oracle()
         dt, T_cpu, st_cpu = cpu_reference_step(orc, pairs[0])
         cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-               "sample": "1 pair (%d/%d points), %.1f s, %d iterations" % (n, m, dt, st_cpu.num_iterations),
+               "sample": "1 pair (%d/%d points), %.1f s, %d iterations" % (len(s0), len(t0), dt, st_cpu.num_iterations),
                "parity_vs_gpu": {"rot_rad": W.rotation_error(T_cpu, T_dev[0]),
                                  "transl": float(np.linalg.norm(T_cpu[:3, 3] - T_dev[0][:3, 3])),
                                  "iterations_cpu": st_cpu.num_iterations, "iterations_gpu": stats[0].num_iterations}}
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 (f32 candidate sweep, exact f64 decisions)", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, pairs, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -279,7 +309,7 @@ def run_b200(args):
             "accuracy": {"max_rot_err_rad_vs_gt": max(e[0] for e in errs), "max_transl_err_m_vs_gt": max(e[1] for e in errs),
                          "pairs_within_2deg_0.25m": int(sum(1 for e in errs if np.degrees(e[0]) <= 2.0 and e[1] <= 0.25)),
                          "pairs": P},
-            "contexts_per_gpu": args.contexts,
+            "contexts_per_gpu": args.contexts, "loop": "one CUDA graph per pair (conditional WHILE node)",
         }
     for c in ctxs:
         c.close()

@@ -94,6 +94,7 @@ typedef struct se3icp_stats {
     double time_before_pure_icp_ms;  /* reference time_before_pure_icp_ (hpp:85) */
     int64_t exact_repairs;           /* queries re-done by the exact FP64 repair kernel */
     int64_t kernel_launches;         /* kernels of this library launched during the run */
+    double time_se3_phase_search_ms; /* device time of the 12-D correspondence stage, summed over the SE(3) iterations */
 } se3icp_stats;
 
 typedef struct se3icp_ctx se3icp_ctx;

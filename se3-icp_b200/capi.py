@@ -64,6 +64,7 @@ class Stats(C.Structure):
         ("time_before_pure_icp_ms", C.c_double),
         ("exact_repairs", C.c_int64),
         ("kernel_launches", C.c_int64),
+        ("time_se3_phase_search_ms", C.c_double),
     ]
 
 

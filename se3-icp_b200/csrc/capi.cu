@@ -608,6 +608,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         cudaEventElapsedTime(&ms, c->ev_begin, c->ev_setup);
         stats->time_setup_ms = ms;
         stats->time_se3_correspondence_search_ms = (double)hs.t_corr_ns / 1e6;
+        stats->time_se3_phase_search_ms = (double)hs.t_corr_se3_ns / 1e6;
         stats->time_before_pure_icp_ms = stats->time_total_ms;  // .cpp:957-958 measures the whole call
         stats->exact_repairs = hs.total_repairs;
         stats->kernel_launches = c->launches + (c->graph_run ? c->launches_per_iter * (long long)hs.iter : 0);

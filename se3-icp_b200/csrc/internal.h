@@ -64,10 +64,11 @@ struct IterState {
     int hist_count;
     int switch_iter;  // value of iter when the ICP phase began (-1 before)
     int work_count;   // entries of the coherence work list (reset every iteration)
-    int pad2;
+    int corr_stamped; // the end of this iteration's correspondence stage has been time-stamped
     long long total_repairs;
     unsigned long long t_mark;      // globaltimer at the end of the previous solve/update
-    unsigned long long t_corr_ns;   // accumulated correspondence-search time
+    unsigned long long t_corr_ns;   // accumulated correspondence-search time (both phases)
+    unsigned long long t_corr_se3_ns;  // ... of which SE(3)-phase iterations (filter + 12-D search kernels)
     unsigned long long t_start;     // globaltimer at state initialisation
     unsigned long long t_switch;    // globaltimer when the ICP phase began
 };

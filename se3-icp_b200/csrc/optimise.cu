@@ -26,6 +26,15 @@ __device__ __forceinline__ bool se3_phase_active_o(const RunConfig& cfg, const I
     return cfg.has_se3 && (cfg.pure || !st->switch_icp);
 }
 
+// called by the first thread of the first kernel that follows the correspondence stage of an iteration
+__device__ __forceinline__ void stamp_correspondence_end(const RunConfig& cfg, IterState* state) {
+    if (state->corr_stamped) return;
+    state->corr_stamped = 1;
+    unsigned long long now = global_timer_ns();
+    state->t_corr_ns += now - state->t_mark;
+    if (se3_phase_active_o(cfg, state)) state->t_corr_se3_ns += now - state->t_mark;
+}
+
 // ------------------------------------------------------------------------------------------------
 // state
 // ------------------------------------------------------------------------------------------------
@@ -55,8 +64,11 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->hist_count = 0;
         st->switch_iter = -1;
         st->work_count = 0;
+    st->corr_stamped = 0;
+        st->corr_stamped = 0;
         st->total_repairs = 0;
         st->t_corr_ns = 0;
+        st->t_corr_se3_ns = 0;
         st->t_start = global_timer_ns();
         st->t_mark = st->t_start;
         st->t_switch = 0;
@@ -122,10 +134,11 @@ __device__ __forceinline__ void trim_prefix(const unsigned int* __restrict__ his
     }
 }
 
-__global__ void __launch_bounds__(256) trim_hist_kernel(RunConfig cfg, const IterState* __restrict__ state,
+__global__ void __launch_bounds__(256) trim_hist_kernel(RunConfig cfg, IterState* __restrict__ state,
                                                          const float* __restrict__ distf, int n, unsigned int* __restrict__ hist,
                                                          int pass) {
     if (state->done) return;
+    if (pass == 0 && blockIdx.x == 0 && threadIdx.x == 0) stamp_correspondence_end(cfg, state);
     __shared__ unsigned int sh[256];
     __shared__ unsigned int s_prefix;
     sh[threadIdx.x] = 0;
@@ -277,11 +290,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
     __shared__ double Tm[16];
     __shared__ double sm[8][kAcc];
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // correspondence search of this iteration ended when this kernel started
-        unsigned long long now = global_timer_ns();
-        state->t_corr_ns += now - state->t_mark;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp_correspondence_end(cfg, state);
     __syncthreads();
     double acc[kAcc];
 #pragma unroll
@@ -655,6 +664,7 @@ __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterSta
     st->total_repairs += st->repair_count;
     st->repair_count = 0;
     st->work_count = 0;
+    st->corr_stamped = 0;
     st->t_mark = global_timer_ns();
 }
 
