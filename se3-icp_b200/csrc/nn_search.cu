@@ -53,6 +53,17 @@ __device__ __forceinline__ double exact_d2_12(const double q[12], const double* 
     return s;
 }
 
+// same, query held in shared memory (frees 24 registers in the traversal kernel)
+__device__ __forceinline__ double exact_d2_12_sm(const double* q, const double* __restrict__ rows64, size_t m, int j) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        double df = __dsub_rn(q[k], rows64[k * m + j]);
+        s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    return s;
+}
+
 __device__ __forceinline__ void write_se3_match(const TargetView& T, const RunConfig& cfg, CorrBuffers& cb, int i,
                                                 const double q[12], int j, double d2_12) {
     const size_t m = (size_t)T.n;
@@ -316,11 +327,12 @@ int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& 
 // ------------------------------------------------------------------------------------------------
 constexpr int kTreeWarps = 8;
 
-__global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
+__global__ void __launch_bounds__(kTreeWarps * 32, 4) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                                        IterState* __restrict__ state, CorrBuffers cb) {
     if (state->done || !se3_phase_active(cfg, state)) return;
     __shared__ int2 stacks[kTreeWarps][kStackEntries];
     __shared__ double Tm[16];
+    __shared__ double qs[kTreeWarps][12];
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -339,8 +351,16 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
     const size_t m = (size_t)M, tn = (size_t)T.idx.total_nodes;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
-    double q[12];
-    make_query(S, cfg, Tm, i, q);
+    double* q = qs[wib];  // the FP64 query lives in shared memory; only its FP32 image stays in registers
+    {
+        double qr[12];
+        make_query(S, cfg, Tm, i, qr);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) q[k] = qr[k];
+        }
+        __syncwarp();
+    }
     // FP32 query with one scalar margin covering its rounding: |q_k - qf_k| <= 2^-24 |q_k| <= qeps
     float qf[12];
     float qamax = 0.f;
@@ -383,7 +403,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
         double d2 = inf;
         int id = 0x7fffffff;
         if (p < M) {
-            d2 = exact_d2_12(q, T.rows64, m, p);
+            d2 = exact_d2_12_sm(q, T.rows64, m, p);
             id = T.perm12[p];
         }
         if (!coherent) {
@@ -421,7 +441,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 3) nn_se3_tree_kernel(SourceV
     if (have_prev && !coherent) {
         best_j = T.inv12[prev];
         best_id = prev;
-        tau = exact_d2_12(q, T.rows64, m, best_j);
+        tau = exact_d2_12_sm(q, T.rows64, m, best_j);
     } else {
         int first;
         if (have_prev) {
