@@ -77,6 +77,7 @@ SourceView se3icp_ctx::source_view() const {
     S.n = (int)n[0];
     S.begin = sharded ? shard_begin : 0;
     S.end = sharded ? shard_end : (int)n[0];
+    S.order = (!sharded && src_index_built) ? index[0].perm.as<int>() : nullptr;
     S.x = index[0].x.as<double>();
     S.y = index[0].y.as<double>();
     S.z = index[0].z.as<double>();
@@ -253,6 +254,7 @@ int enqueue_setup(se3icp_ctx* c) {
     SE3_TRY(c->index[1].build(st, &c->launches));
     const bool need_src_index = cfg.has_se3 || cfg.variant == SE3ICP_GICP;
     if (need_src_index) SE3_TRY(c->index[0].build(st, &c->launches));
+    c->src_index_built = need_src_index;
 
     for (int w = 0; w < 2; w++) {
         FeatureArgs fa{};
@@ -286,7 +288,7 @@ int enqueue_setup(se3icp_ctx* c) {
     return 0;
 }
 
-int enqueue_iteration(se3icp_ctx* c) {
+int enqueue_iteration(se3icp_ctx* c, unsigned long long cond_handle = 0) {
     const RunConfig& cfg = c->cfg;
     cudaStream_t st = c->stream;
     SourceView S = c->source_view();
@@ -295,19 +297,18 @@ int enqueue_iteration(se3icp_ctx* c) {
     IterState* ds = c->dstate();
     SE3_TRY(launch_nn_filter(S, T, cfg, ds, cb, st));
     if (cfg.coherence || cfg.coherence_xyz) c->launches += 1;
-    if (cfg.has_se3) {
-        int mode = c->params.nn_mode;
-        if (mode == SE3ICP_NN_BRUTE_F32 || mode == SE3ICP_NN_EXACT_F64) {
-            SE3_TRY(launch_nn_se3_brute(S, T, cfg, ds, cb, mode == SE3ICP_NN_EXACT_F64, st));
-            SE3_TRY(launch_nn_se3_repair(S, T, cfg, ds, cb, st));
-            c->launches += 2;
-        } else {  // AUTO / TREE: pruned traversal is the default (~10 of 3 730 leaves per query)
-            SE3_TRY(launch_nn_se3_tree(S, T, cfg, ds, cb, st));
+    const int mode = c->params.nn_mode;
+    if (cfg.has_se3 && (mode == SE3ICP_NN_BRUTE_F32 || mode == SE3ICP_NN_EXACT_F64)) {
+        SE3_TRY(launch_nn_se3_brute(S, T, cfg, ds, cb, mode == SE3ICP_NN_EXACT_F64, st));
+        SE3_TRY(launch_nn_se3_repair(S, T, cfg, ds, cb, st));
+        c->launches += 2;
+        if (!cfg.pure) {
+            SE3_TRY(launch_nn_xyz(S, T, cfg, ds, cb, st));
             c->launches += 1;
         }
-    }
-    if (!cfg.pure) {
-        SE3_TRY(launch_nn_xyz(S, T, cfg, ds, cb, st));
+    } else {
+        // AUTO / TREE: pruned traversals; one kernel serves both phases (the phase flag is device-side)
+        SE3_TRY(launch_nn_search(S, T, cfg, ds, cb, st));
         c->launches += 1;
     }
     const bool multi = c->sharded && c->comm && c->comm_size > 1;
@@ -343,11 +344,12 @@ int enqueue_iteration(se3icp_ctx* c) {
         // one all-reduce of the 29-double record per iteration; every rank then runs the identical solve
         SE3_TRY(launch_sum_partials(c->partials.as<double>(), c->totals.as<double>(), st));
         SE3_NCCL(nccl->AllReduce(c->totals.ptr, c->totals.ptr, kReducePartials, ncclFloat64, ncclSum, comm, st));
-        SE3_TRY(launch_solve_update(cfg, ds, c->totals.as<double>(), 1, c->history.as<double>(), c->hist.as<unsigned int>(), st));
+        SE3_TRY(launch_solve_update(cfg, ds, c->totals.as<double>(), 1, c->history.as<double>(), c->hist.as<unsigned int>(),
+                                    cond_handle, st));
         c->launches += 3;
     } else {
         SE3_TRY(launch_solve_update(cfg, ds, c->partials.as<double>(), kReduceBlocks, c->history.as<double>(),
-                                    c->hist.as<unsigned int>(), st));
+                                    c->hist.as<unsigned int>(), cond_handle, st));
         c->launches += 2;
     }
     return 0;
@@ -557,13 +559,12 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
         cudaGraph_t body = np.conditional.phGraph_out[0];
         SE3_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
         long long before = c->launches;
-        int rc = enqueue_iteration(c);
-        if (rc == 0) rc = launch_loop_condition((unsigned long long)handle, c->dstate(), c->stream);
+        int rc = enqueue_iteration(c, (unsigned long long)handle);  // solve_update sets the loop condition
         cudaGraph_t captured = nullptr;
         cudaError_t ce = cudaStreamEndCapture(c->stream, &captured);
         if (rc) return rc;
         SE3_CUDA(ce);
-        c->launches_per_iter = c->launches - before + 1;
+        c->launches_per_iter = c->launches - before;
         c->launches = before;
         SE3_CUDA(cudaGraphInstantiate(&c->loop_exec, c->loop_graph, 0));
         SE3_CUDA(cudaGraphLaunch(c->loop_exec, c->stream));
@@ -1063,6 +1064,7 @@ int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double*
     S.n = (int)n;
     S.begin = 0;
     S.end = (int)n;
+    S.order = nullptr;
     S.x = c->scratch.as<double>();
     S.y = S.x + n;
     S.z = S.x + 2 * n;
@@ -1107,6 +1109,7 @@ int se3icp_nn_xyz(se3icp_ctx* c, const double* queries, size_t n, const double* 
     S.n = (int)n;
     S.begin = 0;
     S.end = (int)n;
+    S.order = nullptr;
     S.x = c->scratch.as<double>();
     S.y = S.x + n;
     S.z = S.x + 2 * n;
@@ -1176,6 +1179,7 @@ int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* sr
     S.n = (int)n;
     S.begin = 0;
     S.end = (int)n;
+    S.order = nullptr;
     S.x = c->scratch.as<double>();
     S.y = S.x + n;
     S.z = S.x + 2 * n;
@@ -1197,7 +1201,7 @@ int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* sr
         }
     }
     if (T_out) {
-        SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), kReduceBlocks, nullptr, c->hist.as<unsigned int>(), c->stream));
+        SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), kReduceBlocks, nullptr, c->hist.as<unsigned int>(), 0, c->stream));
         SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
         SE3_CUDA(cudaStreamSynchronize(c->stream));
         memcpy(T_out, c->h_state->T_i, 16 * sizeof(double));
@@ -1242,7 +1246,7 @@ int se3icp_solve(se3icp_ctx* c, const double* in27, double* T_out) {
     SE3_CUDA(cudaMemcpyAsync(c->partials.ptr, part.data(), part.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     RunConfig cfg;
     identity_config(cfg, SE3ICP_PT2PL, false);
-    SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), kReduceBlocks, nullptr, c->hist.as<unsigned int>(), c->stream));
+    SE3_TRY(launch_solve_update(cfg, c->dstate(), c->partials.as<double>(), kReduceBlocks, nullptr, c->hist.as<unsigned int>(), 0, c->stream));
     SE3_CUDA(cudaMemcpyAsync(c->h_state, c->dstate(), sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
     SE3_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(T_out, c->h_state->T_i, 16 * sizeof(double));

@@ -99,6 +99,7 @@ struct RunConfig {
 struct SourceView {
     int n;                // points in the cloud (plane stride of frame / cov)
     int begin, end;       // query range owned by this rank: [0, n) unless the pair is sharded
+    const int* order;     // optional processing order (a permutation of [0, n): the source's Morton order), or null
     const double* x;      // working-frame original coordinates p0 (never rewritten: q = T_total * p0 on the fly)
     const double* y;
     const double* z;
@@ -168,6 +169,8 @@ int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, dou
 // nn_search.cu
 int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                      cudaStream_t st);
+int launch_nn_search(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                     cudaStream_t st);  // 12-D or 3-D search, chosen on the device by the phase flag
 int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                        cudaStream_t st);
 int launch_nn_se3_brute(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,
@@ -191,7 +194,8 @@ int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg
 int launch_sum_partials(const double* partials /*[kReduceBlocks][kReducePartials]*/, double* total /*[kReducePartials]*/,
                         cudaStream_t st);
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,
-                        unsigned int* hist /*[4*256] trim histograms, zeroed for the next iteration*/, cudaStream_t st);
+                        unsigned int* hist /*[4*256] trim histograms, zeroed for the next iteration*/,
+                        unsigned long long cond_handle /*0 = none*/, cudaStream_t st);
 int launch_loop_condition(unsigned long long cond_handle, const IterState* state, cudaStream_t st);
 int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st);
 int launch_init_state(IterState* state, unsigned int* hist, cudaStream_t st);

@@ -270,8 +270,10 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
     const bool se3 = se3_phase_active(cfg, state);
     const bool enabled = se3 ? cfg.coherence : cfg.coherence_xyz;
     if (!enabled || !(state->T_change < cfg.coherence_thr)) return;
-    const int i = S.begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S.end) return;
+    const int t = S.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.end) return;
+    // spatially sorted processing order: the work list then hands neighbouring queries to neighbouring warps
+    const int i = S.order ? S.order[t] : t;
     const double* Tm = state->T_total;
     const size_t n = (size_t)S.n, m = (size_t)T.n;
     bool settled = false;
@@ -327,14 +329,9 @@ int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& 
 // ------------------------------------------------------------------------------------------------
 constexpr int kTreeWarps = 8;
 
-__global__ void __launch_bounds__(kTreeWarps * 32, 4) nn_se3_tree_kernel(SourceView S, TargetView T, RunConfig cfg,
-                                                                       IterState* __restrict__ state, CorrBuffers cb) {
-    if (state->done || !se3_phase_active(cfg, state)) return;
-    __shared__ int2 stacks[kTreeWarps][kStackEntries];
-    __shared__ double Tm[16];
-    __shared__ double qs[kTreeWarps][12];
-    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
-    __syncthreads();
+__device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetView& T, const RunConfig& cfg,
+                                              IterState* __restrict__ state, CorrBuffers& cb,
+                                              int2 (*stacks)[kStackEntries], const double* Tm, double (*qs)[12]) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // coherent iterations only search the queries the filter kernel could not settle (cb.work list)
     const bool coherent = cfg.coherence && state->T_change < cfg.coherence_thr;
@@ -480,29 +477,12 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4) nn_se3_tree_kernel(SourceV
     }
 }
 
-int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
-                       cudaStream_t st) {
-    if (T.idx.n_levels > 6) {
-        set_last_error("cloud too large for the traversal stack");
-        return SE3ICP_ERR_UNSUPPORTED;
-    }
-    int g = (S.end - S.begin + kTreeWarps - 1) / kTreeWarps;
-    if (g < 1) g = 1;
-    nn_se3_tree_kernel<<<g, kTreeWarps * 32, 0, st>>>(S, T, cfg, state, cb);
-    SE3_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // ------------------------------------------------------------------------------------------------
-constexpr int kXyzWarps = 8;
+constexpr int kXyzWarps = kTreeWarps;
 
-__global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, TargetView T, RunConfig cfg,
-                                                                 IterState* __restrict__ state, CorrBuffers cb) {
-    if (state->done || se3_phase_active(cfg, state)) return;
-    __shared__ int2 stacks[kXyzWarps][kStackEntries];
-    __shared__ double Tm[16];
-    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
-    __syncthreads();
+__device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& T, const RunConfig& cfg,
+                                         IterState* __restrict__ state, CorrBuffers& cb, int2 (*stacks)[kStackEntries],
+                                         const double* Tm) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool coherent = cfg.coherence_xyz && state->T_change < cfg.coherence_thr;
     const int w = blockIdx.x * kXyzWarps + wib;
@@ -599,17 +579,50 @@ __global__ void __launch_bounds__(kXyzWarps * 32) nn_xyz_kernel(SourceView S, Ta
     }
 }
 
-int launch_nn_xyz(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
-                  cudaStream_t st) {
+// One kernel for the correspondence stage of an iteration: the phase flag lives on the device, so the kernel
+// picks the 12-D or the 3-D search itself (which = 0), instead of launching both and letting one early-out.
+// which = 1 / 2 restricts it to the SE(3) / XYZ search (stage-level entry points, timing hook).
+__global__ void __launch_bounds__(kTreeWarps * 32, 4) nn_search_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                                        IterState* __restrict__ state, CorrBuffers cb,
+                                                                        int which) {
+    if (state->done) return;
+    const bool se3 = se3_phase_active(cfg, state);
+    if ((which == 1 && !se3) || (which == 2 && se3)) return;
+    __shared__ int2 stacks[kTreeWarps][kStackEntries];
+    __shared__ double Tm[16];
+    __shared__ double qs[kTreeWarps][12];
+    if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
+    __syncthreads();
+    if (se3)
+        se3_tree_body(S, T, cfg, state, cb, stacks, Tm, qs);
+    else
+        xyz_body(S, T, cfg, state, cb, stacks, Tm);
+}
+
+static int launch_nn_search_which(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state,
+                                  CorrBuffers cb, int which, cudaStream_t st) {
     if (T.idx.n_levels > 6) {
         set_last_error("cloud too large for the traversal stack");
         return SE3ICP_ERR_UNSUPPORTED;
     }
-    int g = (S.end - S.begin + kXyzWarps - 1) / kXyzWarps;
+    int g = (S.end - S.begin + kTreeWarps - 1) / kTreeWarps;
     if (g < 1) g = 1;
-    nn_xyz_kernel<<<g, kXyzWarps * 32, 0, st>>>(S, T, cfg, state, cb);
+    nn_search_kernel<<<g, kTreeWarps * 32, 0, st>>>(S, T, cfg, state, cb, which);
     SE3_CUDA(cudaGetLastError());
     return 0;
+}
+
+int launch_nn_search(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                     cudaStream_t st) {
+    return launch_nn_search_which(S, T, cfg, state, cb, 0, st);
+}
+int launch_nn_se3_tree(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                       cudaStream_t st) {
+    return launch_nn_search_which(S, T, cfg, state, cb, 1, st);
+}
+int launch_nn_xyz(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
+                  cudaStream_t st) {
+    return launch_nn_search_which(S, T, cfg, state, cb, 2, st);
 }
 
 }  // namespace se3

@@ -425,7 +425,10 @@ int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg
 // solve + update (one warp)
 // ------------------------------------------------------------------------------------------------
 // pivoted LDL^T of a symmetric 6x6 (diagonal pivoting, like Eigen::LDLT which Open3D's
-// SolveLinearSystemPSD calls); returns false when the solution is not finite
+// SolveLinearSystemPSD calls); returns false when the solution is not finite.  The pivot swaps are
+// predicated selects over loop indices so the compiler can unroll and keep the factorisation in registers.
+// NOTE: do not add `#pragma unroll` here — nvcc 12.9 miscompiles this function for sm_100a when the loops
+// are force-unrolled (verified against the host build of the same source; plain -O3 is correct).
 __device__ bool ldlt6_solve(const double Ain[6][6], const double bin[6], double x[6]) {
     double A[6][6], L[6][6], D[6], b[6];
     int perm[6];
@@ -440,34 +443,56 @@ __device__ bool ldlt6_solve(const double Ain[6][6], const double bin[6], double 
     for (int k = 0; k < 6; k++) {
         int piv = k;
         double big = fabs(A[k][k]);
-        for (int i = k + 1; i < 6; i++)
-            if (fabs(A[i][i]) > big) {
-                big = fabs(A[i][i]);
+        for (int i = k + 1; i < 6; i++) {
+            double v = fabs(A[i][i]);
+            if (v > big) {
+                big = v;
                 piv = i;
             }
-        if (piv != k) {
-            for (int j = 0; j < 6; j++) { double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
-            for (int i = 0; i < 6; i++) { double t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
-            for (int j = 0; j < k; j++) { double t = L[k][j]; L[k][j] = L[piv][j]; L[piv][j] = t; }
-            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        for (int i = k + 1; i < 6; i++) {
+            const bool sw = piv == i;  // at most one i matches
+            for (int j = 0; j < 6; j++) {  // rows k <-> i
+                double t = A[k][j], u = A[i][j];
+                A[k][j] = sw ? u : t;
+                A[i][j] = sw ? t : u;
+            }
+            for (int r = 0; r < 6; r++) {  // columns k <-> i
+                double t = A[r][k], u = A[r][i];
+                A[r][k] = sw ? u : t;
+                A[r][i] = sw ? t : u;
+            }
+            for (int j = 0; j < k; j++) {
+                double t = L[k][j], u = L[i][j];
+                L[k][j] = sw ? u : t;
+                L[i][j] = sw ? t : u;
+            }
+            int tp = perm[k], up = perm[i];
+            perm[k] = sw ? up : tp;
+            perm[i] = sw ? tp : up;
         }
         D[k] = A[k][k];
         L[k][k] = 1.0;
-        if (D[k] == 0.0) continue;
-        for (int i = k + 1; i < 6; i++) L[i][k] = A[i][k] / D[k];
+        const bool nz = D[k] != 0.0;
+        for (int i = k + 1; i < 6; i++) L[i][k] = nz ? A[i][k] / D[k] : 0.0;
         for (int i = k + 1; i < 6; i++)
-            for (int j = k + 1; j < 6; j++) A[i][j] -= L[i][k] * D[k] * L[j][k];
+            for (int j = k + 1; j < 6; j++) A[i][j] = nz ? A[i][j] - L[i][k] * D[k] * L[j][k] : A[i][j];
     }
     double y[6], z[6];
-    for (int i = 0; i < 6; i++) y[i] = b[perm[i]];
+    for (int i = 0; i < 6; i++) {  // y = P b (perm is data dependent: select)
+        double v = 0.0;
+        for (int j = 0; j < 6; j++) v = perm[i] == j ? b[j] : v;
+        y[i] = v;
+    }
     for (int i = 0; i < 6; i++)
         for (int j = 0; j < i; j++) y[i] -= L[i][j] * y[j];
     for (int i = 0; i < 6; i++) z[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
     for (int i = 5; i >= 0; i--)
         for (int j = i + 1; j < 6; j++) z[i] -= L[j][i] * z[j];
     bool ok = true;
+    for (int j = 0; j < 6; j++) x[j] = 0.0;
     for (int i = 0; i < 6; i++) {
-        x[perm[i]] = z[i];
+        for (int j = 0; j < 6; j++) x[j] = perm[i] == j ? z[i] : x[j];
         ok = ok && isfinite(z[i]);
     }
     return ok;
@@ -561,21 +586,36 @@ int launch_sum_partials(const double* partials, double* total, cudaStream_t st) 
     return 0;
 }
 
-__global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterState* __restrict__ st,
-                                                           const double* __restrict__ partials, int n_records,
-                                                           double* __restrict__ history, unsigned int* __restrict__ hist) {
-    if (st->done) return;
+// cond_handle != 0: this kernel is the last node of the captured loop body and tells the WHILE node whether
+// to run it again
+__global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterState* __restrict__ st,
+                                                            const double* __restrict__ partials, int n_records,
+                                                            double* __restrict__ history, unsigned int* __restrict__ hist,
+                                                            unsigned long long cond_handle) {
+    if (st->done) {
+        if (cond_handle && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
+        return;
+    }
     __shared__ double tot[kReducePartials];
-    const int lane = threadIdx.x;
-    if (lane < kAcc) {
+    __shared__ double wsum[8][kReducePartials];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    {   // fixed-order sum of the per-block records: warp w takes records w, w+8, ...; then the 8 warp sums in order
         double s = 0.0;
-        for (int b = 0; b < n_records; b++) s += partials[b * kReducePartials + lane];  // fixed order
-        tot[lane] = s;
+        if (lane < kAcc)
+            for (int b = w; b < n_records; b += 8) s += partials[b * kReducePartials + lane];
+        wsum[w][lane] = s;
     }
     if (hist)
-        for (int k = lane; k < 4 * 256; k += 32) hist[k] = 0;  // ready for the next iteration's trim
-    __syncwarp();
-    if (lane != 0) return;
+        for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) hist[k] = 0;  // ready for the next iteration's trim
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += wsum[k][threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
 
     const double K = tot[28];
     const double mean = tot[27] / K;  // 0/0 -> NaN exactly as the reference
@@ -666,11 +706,12 @@ __global__ void __launch_bounds__(32) solve_update_kernel(RunConfig cfg, IterSta
     st->work_count = 0;
     st->corr_stamped = 0;
     st->t_mark = global_timer_ns();
+    if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, st->done ? 0u : 1u);
 }
 
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,
-                        unsigned int* hist, cudaStream_t st) {
-    solve_update_kernel<<<1, 32, 0, st>>>(cfg, state, partials, n_records, history, hist);
+                        unsigned int* hist, unsigned long long cond_handle, cudaStream_t st) {
+    solve_update_kernel<<<1, 256, 0, st>>>(cfg, state, partials, n_records, history, hist, cond_handle);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }
