@@ -5,8 +5,12 @@
 // is done by libse3icp_cuda.so, not here.
 #pragma once
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <numeric>
+#include <random>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -19,7 +23,27 @@
 
 namespace open3d {
 
+namespace utility {
+namespace random {
+inline std::mt19937& Engine() {
+    static std::mt19937 e(0);
+    return e;
+}
+inline void Seed(int seed) { Engine().seed((unsigned)seed); }
+}  // namespace random
+}  // namespace utility
+
 namespace geometry {
+
+class KDTreeSearchParam {
+public:
+    virtual ~KDTreeSearchParam() {}
+};
+class KDTreeSearchParamKNN : public KDTreeSearchParam {
+public:
+    KDTreeSearchParamKNN(int knn = 30) : knn_(knn) {}
+    int knn_;
+};
 
 class PointCloud {
 public:
@@ -57,14 +81,133 @@ public:
         for (auto& C : covariances_) C = R * C * R.transpose();
         return *this;
     }
+    // random subset of round(ratio * n) points, seeded through utility::random::Seed (the index stream differs
+    // from Open3D's, the statistics do not)
+    std::shared_ptr<PointCloud> RandomDownSample(double sampling_ratio) const {
+        auto out = std::make_shared<PointCloud>();
+        std::vector<size_t> idx(points_.size());
+        std::iota(idx.begin(), idx.end(), 0);
+        std::shuffle(idx.begin(), idx.end(), utility::random::Engine());
+        size_t n = (size_t)((double)points_.size() * sampling_ratio);
+        idx.resize(std::min(n, idx.size()));
+        for (size_t i : idx) out->points_.push_back(points_[i]);
+        return out;
+    }
+    // Only the FGR baselines and diagnostics of the reference's drivers call these (out of scope);
+    // the registration path computes its normals on the GPU.
+    void EstimateNormals(const KDTreeSearchParam& = KDTreeSearchParamKNN(), bool = true) {
+        std::cerr << "[compat] open3d::geometry::PointCloud::EstimateNormals is not provided by the stand-in\n";
+    }
+    inline std::vector<double> ComputePointCloudDistance(const PointCloud& target) const;
+    PointCloud& PaintUniformColor(const Eigen::Vector3d&) { return *this; }
 };
 
-// member type only: the spatial index lives on the GPU
+// The registration path never searches this tree (its spatial indices live on the GPU); the stand-in is a plain
+// CPU kd-tree so that the reference's evaluation helpers (src/cc.cpp:116-143,220-237) still work.
 class KDTreeFlann {
 public:
     KDTreeFlann() = default;
-    bool SetGeometry(const PointCloud&) { return true; }
+    explicit KDTreeFlann(const PointCloud& pc) { SetGeometry(pc); }
+    bool SetGeometry(const PointCloud& pc) {
+        pts_ = pc.points_;
+        perm_.resize(pts_.size());
+        std::iota(perm_.begin(), perm_.end(), 0);
+        nodes_.clear();
+        if (!pts_.empty()) Build(0, (int)pts_.size());
+        return true;
+    }
+    int SearchKNN(const Eigen::Vector3d& q, int knn, std::vector<int>& indices, std::vector<double>& distance2) const {
+        std::vector<std::pair<double, int>> heap;
+        if (!nodes_.empty() && knn > 0) Search(0, q, (size_t)knn, 1e300, heap);
+        std::sort_heap(heap.begin(), heap.end());
+        indices.resize(heap.size());
+        distance2.resize(heap.size());
+        for (size_t i = 0; i < heap.size(); i++) {
+            indices[i] = heap[i].second;
+            distance2[i] = heap[i].first;
+        }
+        return (int)heap.size();
+    }
+    int SearchRadius(const Eigen::Vector3d& q, double radius, std::vector<int>& indices, std::vector<double>& distance2) const {
+        std::vector<std::pair<double, int>> heap;
+        if (!nodes_.empty()) Search(0, q, pts_.size(), radius * radius, heap);
+        std::sort_heap(heap.begin(), heap.end());
+        indices.clear();
+        distance2.clear();
+        for (auto& h : heap) {
+            indices.push_back(h.second);
+            distance2.push_back(h.first);
+        }
+        return (int)heap.size();
+    }
+
+private:
+    struct Node {
+        int left = -1, right = -1, dim = -1, begin = 0, end = 0;
+        double split = 0;
+    };
+    std::vector<Eigen::Vector3d> pts_;
+    std::vector<int> perm_;
+    std::vector<Node> nodes_;
+    int Build(int b, int e) {
+        int id = (int)nodes_.size();
+        nodes_.emplace_back();
+        nodes_[id].begin = b;
+        nodes_[id].end = e;
+        if (e - b <= 16) return id;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = b; i < e; i++)
+            for (int d = 0; d < 3; d++) {
+                lo[d] = std::min(lo[d], pts_[perm_[i]][d]);
+                hi[d] = std::max(hi[d], pts_[perm_[i]][d]);
+            }
+        int dim = 0;
+        for (int d = 1; d < 3; d++)
+            if (hi[d] - lo[d] > hi[dim] - lo[dim]) dim = d;
+        int mid = (b + e) / 2;
+        std::nth_element(perm_.begin() + b, perm_.begin() + mid, perm_.begin() + e,
+                         [&](int x, int y) { return pts_[x][dim] < pts_[y][dim]; });
+        nodes_[id].dim = dim;
+        nodes_[id].split = pts_[perm_[mid]][dim];
+        int l = Build(b, mid);
+        int r = Build(mid, e);
+        nodes_[id].left = l;
+        nodes_[id].right = r;
+        return id;
+    }
+    void Search(int id, const Eigen::Vector3d& q, size_t k, double max_d2, std::vector<std::pair<double, int>>& heap) const {
+        const Node& nd = nodes_[id];
+        if (nd.dim < 0) {
+            for (int i = nd.begin; i < nd.end; i++) {
+                double d2 = (pts_[perm_[i]] - q).squaredNorm();
+                if (d2 > max_d2) continue;
+                if (heap.size() < k) {
+                    heap.emplace_back(d2, perm_[i]);
+                    std::push_heap(heap.begin(), heap.end());
+                } else if (d2 < heap.front().first) {
+                    std::pop_heap(heap.begin(), heap.end());
+                    heap.back() = {d2, perm_[i]};
+                    std::push_heap(heap.begin(), heap.end());
+                }
+            }
+            return;
+        }
+        double diff = q[nd.dim] - nd.split;
+        int near = diff < 0 ? nd.left : nd.right, far = diff < 0 ? nd.right : nd.left;
+        Search(near, q, k, max_d2, heap);
+        double bound = heap.size() < k ? max_d2 : std::min(max_d2, heap.front().first);
+        if (diff * diff <= bound) Search(far, q, k, max_d2, heap);
+    }
 };
+
+inline std::vector<double> PointCloud::ComputePointCloudDistance(const PointCloud& target) const {
+    std::vector<double> out(points_.size());
+    KDTreeFlann tree(target);
+    std::vector<int> idx;
+    std::vector<double> d2;
+    for (size_t i = 0; i < points_.size(); i++) out[i] = tree.SearchKNN(points_[i], 1, idx, d2) ? std::sqrt(d2[0]) : 0.0;
+    return out;
+}
 
 }  // namespace geometry
 
@@ -75,14 +218,38 @@ typedef std::vector<Eigen::Vector2i> CorrespondenceSet;
 class TransformationEstimationPointToPoint {};
 class TransformationEstimationPointToPlane {};
 class TransformationEstimationForGeneralizedICP {};
+
+// FPFH + Fast Global Registration are a different algorithm (baseline branches of the reference's drivers,
+// OUT OF SCOPE in SURVEY §2.1).  The stand-ins let those translation units compile; calling them reports it.
+class Feature {};
+class FastGlobalRegistrationOption {};
+class RegistrationResult {
+public:
+    Eigen::Matrix4d transformation_ = Eigen::Matrix4d::Identity();
+    double fitness_ = 0.0, inlier_rmse_ = 0.0;
+};
+inline std::shared_ptr<Feature> ComputeFPFHFeature(const geometry::PointCloud&, const geometry::KDTreeSearchParam& =
+                                                                                    geometry::KDTreeSearchParamKNN()) {
+    std::cerr << "[compat] FPFH features are not provided by the stand-in (FGR baseline is out of scope)\n";
+    return std::make_shared<Feature>();
+}
+inline RegistrationResult FastGlobalRegistrationBasedOnFeatureMatching(const geometry::PointCloud&, const geometry::PointCloud&,
+                                                                       const Feature&, const Feature&,
+                                                                       const FastGlobalRegistrationOption& =
+                                                                           FastGlobalRegistrationOption()) {
+    std::cerr << "[compat] Fast Global Registration is not provided by the stand-in; returning identity\n";
+    return RegistrationResult();
+}
 }  // namespace registration
 }  // namespace pipelines
 
-namespace utility {
-namespace random {
-inline void Seed(int) {}
-}  // namespace random
-}  // namespace utility
+namespace visualization {
+inline bool DrawGeometries(const std::vector<std::shared_ptr<const geometry::PointCloud>>&, const std::string& = "Open3D",
+                           int = 640, int = 480, int = 50, int = 50) {
+    std::cerr << "[compat] open3d::visualization is not provided by the stand-in\n";
+    return false;
+}
+}  // namespace visualization
 
 namespace io {
 

@@ -215,3 +215,108 @@ def rgbd_pair(seed=0, width=640, height=480, f=525.0, stride=1):
 
 LOUNGE_PARAMS = dict(estimated_overlap=0.75, mse_switch_error=5e-5, max_num_se3_iterations=10,
                      number_of_nn_for_LRF=90)  # benchmark_lounge.cpp:183-186
+
+
+# --------------------------------------------------------------------------------------------------
+# on-disk datasets in the layouts the reference's benchmark drivers read (tests of the unchanged drivers)
+# --------------------------------------------------------------------------------------------------
+def write_ply(path, pts, dtype="<f8"):
+    """binary little-endian PLY with x/y/z (double by default, as Open3D writes the bundled fixture)"""
+    name = {"<f8": "double", "<f4": "float"}[dtype]
+    with open(path, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\nelement vertex %d\n"
+                 "property %s x\nproperty %s y\nproperty %s z\nend_header\n" % (len(pts), name, name, name)).encode())
+        f.write(np.ascontiguousarray(pts, dtype=dtype).tobytes())
+
+
+def _row12(T):
+    return " ".join("%.12e" % v for v in T[:3].reshape(-1))
+
+
+def write_synthetic_dataset(folder, problems):
+    """examples/benchmark_synthetic.cpp:300-345: <folder>/gt_data (12 numbers per line), source<i>.ply, target<i>.ply"""
+    os.makedirs(folder, exist_ok=True)
+    with open(os.path.join(folder, "gt_data"), "w") as f:
+        for i, (src, tgt, T) in enumerate(problems):
+            f.write(_row12(T) + "\n")
+            write_ply(os.path.join(folder, "source%d.ply" % i), src)
+            write_ply(os.path.join(folder, "target%d.ply" % i), tgt)
+
+
+def write_kitti_dataset(folder, seed=0, n_rings=16, n_az=300):
+    """examples/benchmark_kitti.cpp:70-108: <folder>/Sequence_07/07.txt (poses on every other line) and
+    Sequence_07/Downsampled/000000.ply ... 001100.ply (every 2nd scan, 551 files).  Small synthetic scans of one
+    static street scene along a gently curving trajectory.  Returns the list of poses."""
+    rng = np.random.default_rng(3000 + seed)
+    boxes, cyl = _street_scene(rng)
+    seq = os.path.join(folder, "Sequence_07")
+    os.makedirs(os.path.join(seq, "Downsampled"), exist_ok=True)
+    poses = []
+    pose = make_T(rot_3d(0, 0, 0), [-50.0, 0.0, 0.0])
+    with open(os.path.join(seq, "07.txt"), "w") as f:
+        for k in range(551):
+            poses.append(pose.copy())
+            f.write(_row12(pose) + "\n")
+            f.write("unused line (the driver reads every other line)\n")
+            pts = _lidar_scan(pose, boxes, cyl, rng, n_rings, n_az, 80.0, 0.01)
+            write_ply(os.path.join(seq, "Downsampled", "%06d.ply" % (2 * k)), pts)
+            step = make_T(rot_3d(0, 0, np.deg2rad(rng.uniform(-1.0, 1.0))), [rng.uniform(0.15, 0.22), 0.0, 0.0])
+            pose = pose @ step
+    return poses
+
+
+def _rgbd_scene(rng):
+    room = np.array([[-2.5, -1.4, -0.5, 2.5, 1.4, 3.7]])
+    boxes = []
+    for _ in range(10):
+        cx, cz = rng.uniform(-2.0, 2.0), rng.uniform(1.2, 3.2)
+        w, h, d = rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.2), rng.uniform(0.3, 0.9)
+        boxes.append((cx - w / 2, 1.4 - h, cz - d / 2, cx + w / 2, 1.4, cz + d / 2))
+    return room, np.array(boxes)
+
+
+def _rgbd_render(pose, room, boxes, rng, width=640, height=480, f=525.0, stride=8):
+    u, v = np.meshgrid(np.arange(0, width, stride), np.arange(0, height, stride))
+    d_c = np.stack([(u - width / 2 + 0.5) / f, (v - height / 2 + 0.5) / f, np.ones_like(u, dtype=float)], -1).reshape(-1, 3)
+    o = pose[:3, 3]
+    d_w = d_c @ pose[:3, :3].T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / d_w
+    t0 = (room[0, :3] - o) * inv
+    t1 = (room[0, 3:] - o) * inv
+    best = np.nanmin(np.maximum(t0, t1), axis=1)
+    for b in boxes:
+        t0 = (b[:3] - o) * inv
+        t1 = (b[3:] - o) * inv
+        tmin = np.nanmax(np.minimum(t0, t1), axis=1)
+        tmax = np.nanmin(np.maximum(t0, t1), axis=1)
+        hit = (tmax >= tmin) & (tmin > 0)
+        best = np.where(hit & (tmin < best), tmin, best)
+    z = best
+    sig = 0.002203 * z * z - 0.001028 * z + 0.0005351
+    z = z + rng.normal(0, 1, z.shape) * sig
+    ok = (z > 0.4) & (z < 4.0)
+    return d_c[ok] * z[ok, None]
+
+
+def write_lounge_dataset(folder, seed=0, stride=8):
+    """examples/benchmark_lounge.cpp:142-175: <folder>/lounge_data/lounge_trajectory.log (redwood format: a line
+    with three integers, then the 4x4 camera-to-world matrix) and 00000i.ply for i = 1, 6, ..., 396."""
+    rng = np.random.default_rng(4000 + seed)
+    room, boxes = _rgbd_scene(rng)
+    d = os.path.join(folder, "lounge_data")
+    os.makedirs(d, exist_ok=True)
+    poses = []
+    pose = make_T(rot_3d(0.0, -0.25, 0.0), [-0.8, 0.0, -0.2])
+    with open(os.path.join(d, "lounge_trajectory.log"), "w") as f:
+        for k in range(401):  # frame k+1 of the driver's numbering
+            poses.append(pose.copy())
+            f.write("%d %d %d\n" % (k, k, k + 1))
+            for r in range(4):
+                f.write(" ".join("%.10f" % v for v in pose[r]) + "\n")
+            if k % 5 == 0 and k <= 395:
+                write_ply(os.path.join(d, "%06d.ply" % (k + 1)), _rgbd_render(pose, room, boxes, rng, stride=stride))
+            step = make_T(rot_3d(rng.uniform(-0.002, 0.002), 0.0025 + rng.uniform(-0.001, 0.001), rng.uniform(-0.002, 0.002)),
+                          [0.004, rng.uniform(-0.001, 0.001), 0.001])
+            pose = pose @ step
+    return poses
