@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <utility>
 
 #include "se3icp.h"
 
@@ -28,6 +30,52 @@ const double* xyz_ptr(const open3d::geometry::PointCloud& c) {
 
 void report(const char* where, int rc) {
     std::cerr << "[se3icp] " << where << " failed with status " << rc << ": " << se3icp_last_error() << std::endl;
+}
+
+// The reference's drivers build a fresh IterativeSE3Registration per pair (benchmark_kitti.cpp:128).  Creating a
+// CUDA context object (stream, pinned buffers, device allocations) costs ~40 ms, a registration of a small cloud
+// ~3 ms, so contexts are recycled through a process-wide pool: a destroyed object parks its context (with its
+// grown device buffers) and the next object on the same device picks it up.
+class ContextPool {
+public:
+    se3icp_ctx* acquire(int device) {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].first == device) {
+                    se3icp_ctx* c = free_[i].second;
+                    free_.erase(free_.begin() + (long)i);
+                    return c;
+                }
+        }
+        se3icp_ctx* c = nullptr;
+        int rc = se3icp_create(device, nullptr, &c);
+        if (rc != SE3ICP_OK) {
+            report("se3icp_create", rc);
+            return nullptr;
+        }
+        return c;
+    }
+    void release(int device, se3icp_ctx* c) {
+        if (!c) return;
+        std::lock_guard<std::mutex> lock(mu_);
+        if (free_.size() < 16)
+            free_.emplace_back(device, c);
+        else
+            se3icp_destroy(c);
+    }
+    ~ContextPool() {
+        for (auto& f : free_) se3icp_destroy(f.second);
+    }
+
+private:
+    std::mutex mu_;
+    std::vector<std::pair<int, se3icp_ctx*>> free_;
+};
+
+ContextPool& pool() {
+    static ContextPool p;
+    return p;
 }
 
 Eigen::Matrix4d from_row_major(const double* T) {
@@ -66,26 +114,18 @@ IterativeSE3Registration::IterativeSE3Registration()
     device_ = dev ? std::atoi(dev) : 0;
 }
 
-IterativeSE3Registration::~IterativeSE3Registration() {
-    if (ctx_) se3icp_destroy(ctx_);
-}
+IterativeSE3Registration::~IterativeSE3Registration() { pool().release(device_, ctx_); }
 
 void IterativeSE3Registration::set_device(int device) {
     if (ctx_ && device != device_) {
-        se3icp_destroy(ctx_);
+        pool().release(device_, ctx_);
         ctx_ = nullptr;
     }
     device_ = device;
 }
 
 se3icp_ctx* IterativeSE3Registration::context() {
-    if (!ctx_) {
-        int rc = se3icp_create(device_, nullptr, &ctx_);
-        if (rc != SE3ICP_OK) {
-            report("se3icp_create", rc);
-            ctx_ = nullptr;
-        }
-    }
+    if (!ctx_) ctx_ = pool().acquire(device_);
     return ctx_;
 }
 

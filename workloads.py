@@ -229,6 +229,21 @@ def write_ply(path, pts, dtype="<f8"):
         f.write(np.ascontiguousarray(pts, dtype=dtype).tobytes())
 
 
+def read_ply_xyz(path):
+    """reads back what write_ply wrote"""
+    with open(path, "rb") as f:
+        n, dt = 0, "<f8"
+        while True:
+            line = f.readline().decode().strip()
+            if line.startswith("element vertex"):
+                n = int(line.split()[-1])
+            if line.startswith("property float"):
+                dt = "<f4"
+            if line == "end_header":
+                break
+        return np.frombuffer(f.read(n * 3 * np.dtype(dt).itemsize), dtype=dt).reshape(n, 3).astype(np.float64)
+
+
 def _row12(T):
     return " ".join("%.12e" % v for v in T[:3].reshape(-1))
 
