@@ -126,6 +126,16 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
+def use_all_host_threads(orc):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    orc.set_num_threads(n)
+    return orc.num_threads()
+
+
 def cpu_reference_step(orc, pair):
     src, tgt, _ = pair
     t0 = time.perf_counter()
@@ -139,6 +149,7 @@ def run_reference(args):
     if rank != 0:
         return
     orc = graft.load_oracle()
+    use_all_host_threads(orc)
     pairs = [W.lidar_pair(seed=i, n_az=args.n_az) for i in range(min(UNIQUE_PAIRS, args.steps + args.warmup))]
     for w in range(args.warmup):
         cpu_reference_step(orc, pairs[w % len(pairs)])
@@ -287,6 +298,7 @@ def run_b200(args):
                     "stage_ms": stage_ms}
         # CPU baseline: the oracle port on one full-size pair of the same workload
         orc = graft.load_oracle()
+        use_all_host_threads(orc)
         dt, T_cpu, st_cpu = cpu_reference_step(orc, pairs[0])
         cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                "sample": "1 pair (%d/%d points), %.1f s, %d iterations" % (len(s0), len(t0), dt, st_cpu.num_iterations),
