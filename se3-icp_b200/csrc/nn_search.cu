@@ -393,13 +393,37 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     int prev = cb.idx[i];
     const bool have_prev = prev >= 0 && prev < M;
 
+    // FP32 pre-filter of the leaf rows: |d32 - d2| <= eps(d32) (rounding of the 24 inputs, delta per coordinate
+    // difference, plus the 24 FP32 operations; same bound as the certified sweep, slightly inflated).  Only rows
+    // that could still beat the current bound pay for the exact FP64 evaluation, which decides.
+    const float fdelta = (qamax + (float)state->tgt_absmax) * 5.9604645e-08f * 1.0001f;
     int skip_leaf = -1;
     auto leaf_fn = [&](int leaf) {
         if (leaf == skip_leaf) return;
         int p = leaf * 32 + lane;
+        bool cand = false;
+        if (p < M) {
+            const float4 a = T.rows32[p], b = T.rows32[m + p], c = T.rows32[2 * m + p];
+            float e, d32;
+            e = qf[0] - a.x;  d32 = e * e;
+            e = qf[1] - a.y;  d32 = fmaf(e, e, d32);
+            e = qf[2] - a.z;  d32 = fmaf(e, e, d32);
+            e = qf[3] - a.w;  d32 = fmaf(e, e, d32);
+            e = qf[4] - b.x;  d32 = fmaf(e, e, d32);
+            e = qf[5] - b.y;  d32 = fmaf(e, e, d32);
+            e = qf[6] - b.z;  d32 = fmaf(e, e, d32);
+            e = qf[7] - b.w;  d32 = fmaf(e, e, d32);
+            e = qf[8] - c.x;  d32 = fmaf(e, e, d32);
+            e = qf[9] - c.y;  d32 = fmaf(e, e, d32);
+            e = qf[10] - c.z; d32 = fmaf(e, e, d32);
+            e = qf[11] - c.w; d32 = fmaf(e, e, d32);
+            float eps = d32 * 3.8146973e-06f + 9.f * fdelta * sqrtf(d32) + 20.f * fdelta * fdelta;
+            cand = (double)(d32 - eps) <= (coherent ? b2 : tau);
+        }
+        if (__ballot_sync(SE3_FULL, cand) == 0u) return;
         double d2 = inf;
         int id = 0x7fffffff;
-        if (p < M) {
+        if (cand) {
             d2 = exact_d2_12_sm(q, T.rows64, m, p);
             id = T.perm12[p];
         }
