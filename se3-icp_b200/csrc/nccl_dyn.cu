@@ -12,9 +12,10 @@ const NcclApi* nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
-        void* h = dlopen("libnccl.so.2", RTLD_NOLOAD | RTLD_NOW | RTLD_GLOBAL);  // already in the process?
-        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        // RTLD_LOCAL: a later `import torch` in the same process must stay free to load its own bundled NCCL
+        void* h = dlopen("libnccl.so.2", RTLD_NOLOAD | RTLD_NOW | RTLD_LOCAL);  // already in the process?
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (!h) return;
         api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
