@@ -95,6 +95,28 @@ def lib():
     return _lib
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """The C library resolves NCCL with dlopen("libnccl.so.2").  In a Python process that will also import torch,
+    the copy bundled with torch (nvidia-nccl-cu12) must be the one that gets loaded: once the older system
+    libnccl.so.2 is mapped, the loader reuses it for torch and libtorch_cuda.so fails on missing symbols."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec is not None and spec.submodule_search_locations:
+            path = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+    except Exception:
+        pass  # fall back to whatever libnccl.so.2 the loader finds
+
+
 def _check(rc):
     if rc != 0:
         raise Se3IcpError(rc, lib().se3icp_last_error().decode("utf-8", "replace"))
@@ -203,6 +225,7 @@ class Context:
     # ---- one large pair sharded over ranks --------------------------------------------------------
     def comm_init(self, n_ranks, rank, comm_id):
         """comm_id: the COMM_ID_BYTES produced by comm_unique_id() on one rank and broadcast to all"""
+        _preload_nccl()
         buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
         _check(lib().se3icp_comm_init(self._h, int(n_ranks), int(rank), buf))
 
@@ -314,6 +337,7 @@ class Context:
 
 
 def comm_unique_id():
+    _preload_nccl()
     buf = (C.c_char * COMM_ID_BYTES)()
     _check(lib().se3icp_comm_unique_id(buf))
     return bytes(buf)

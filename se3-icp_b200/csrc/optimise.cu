@@ -588,14 +588,24 @@ int launch_sum_partials(const double* partials, double* total, cudaStream_t st) 
 
 // cond_handle != 0: this kernel is the last node of the captured loop body and tells the WHILE node whether
 // to run it again
-__global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterState* __restrict__ st,
+__global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterState* __restrict__ gst,
                                                             const double* __restrict__ partials, int n_records,
                                                             double* __restrict__ history, unsigned int* __restrict__ hist,
                                                             unsigned long long cond_handle) {
-    if (st->done) {
+    if (gst->done) {
         if (cond_handle && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
         return;
     }
+    // The bookkeeping below touches the state ~150 times from one thread; work on a shared-memory copy (one
+    // parallel load, one parallel store) instead of a chain of dependent global accesses.
+    static_assert(sizeof(IterState) % 8 == 0, "IterState is copied as 64-bit words");
+    __shared__ IterState s_state;
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gst);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_state);
+        for (int k = threadIdx.x; k < (int)(sizeof(IterState) / 8); k += blockDim.x) dst[k] = src[k];
+    }
+    IterState* st = &s_state;
     __shared__ double tot[kReducePartials];
     __shared__ double wsum[8][kReducePartials];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -615,8 +625,7 @@ __global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterSt
         tot[threadIdx.x] = s;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-
+    if (threadIdx.x == 0) {
     const double K = tot[28];
     const double mean = tot[27] / K;  // 0/0 -> NaN exactly as the reference
     double Ti[16];
@@ -707,6 +716,13 @@ __global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterSt
     st->corr_stamped = 0;
     st->t_mark = global_timer_ns();
     if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, st->done ? 0u : 1u);
+    }  // thread 0
+    __syncthreads();
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_state);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(gst);
+        for (int k = threadIdx.x; k < (int)(sizeof(IterState) / 8); k += blockDim.x) dst[k] = src[k];
+    }
 }
 
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,
