@@ -35,7 +35,7 @@ import workloads as W  # noqa: E402
 METRIC = "SE(3)-ICP registrations/s @KITTI-size clouds (se3_gicp)"
 UNIT = "registrations/s"
 UNIQUE_PAIRS = 8  # distinct synthetic scenes per GPU, cycled to pairs_per_gpu
-NCU_TRAFFIC_BYTES = 25224704  # see roofline.traffic below
+NCU_TRAFFIC_BYTES = 32661504  # see roofline.traffic below
 
 
 def parse():
@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=32)
-    ap.add_argument("--contexts", type=int, default=4, help="concurrent registration contexts (streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=8, help="concurrent registration contexts (streams) per GPU")
     ap.add_argument("--n-az", type=int, default=1900, help="azimuth steps of the synthetic 64-ring scanner")
     return ap.parse_args()
 
@@ -285,10 +285,10 @@ def run_b200(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (ms_nn * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of nn_se3_tree_kernel, first (cold) launch of a pair,
-                    # ncu --set full capture summarised in profiles/r1_summary_v1.md
+                    # dram__bytes_read.sum + dram__bytes_write.sum of nn_search_kernel, first launch of a pair (full 12-D
+                    # search of every query), ncu --set full capture summarised in profiles/r1_summary_v4.md
                     "traffic": NCU_TRAFFIC_BYTES,
-                    "kernel": "SE(3) correspondence stage: nn_filter_kernel + nn_se3_tree_kernel",
+                    "kernel": "SE(3) correspondence stage: nn_filter_kernel + nn_search_kernel",
                     "algorithmic_bytes": alg_bytes, "kernel_ms": ms_nn, "launches_averaged": se3_launches,
                     "peak_source": peak_src, "queries_per_s": n / (ms_nn * 1e-3),
                     "note": "exact 12-D search over L2-resident clouds: pointer-chasing, ~0 DRAM traffic by design; "
