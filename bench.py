@@ -136,6 +136,30 @@ def use_all_host_threads(orc):
     return orc.num_threads()
 
 
+def reference_source_build_step(pair, T_gpu):
+    """One pair through oracle/_ref/libse3icp_reference.so — the reference's own source compiled by oracle/Makefile
+    against stand-in Open3D/PCL/Eigen (compat/ + oracle/refdeps/).  Reported next to the oracle port; the port is the
+    baseline because it is the faster of the two (the stand-in linear algebra is naive).  None when the library did
+    not travel (it is built where /root/reference exists)."""
+    sys.path.insert(0, ROOT)
+    from oracle import reference_build as RB
+    if not os.path.exists(RB.LIB_PATH):
+        return None
+    devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)  # the reference prints progress on stdout
+    sys.stdout.flush()
+    os.dup2(devnull, 1)
+    try:
+        t = time.perf_counter()
+        T, it, it_se3 = RB.run("run_se3_icp", "gicp", pair[0], pair[1], RB.default_params(**W.KITTI_PARAMS))
+        dt = time.perf_counter() - t
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    return {"value": 1.0 / dt, "unit": UNIT, "sample": "1 pair, %.1f s" % dt, "iterations": it,
+            "rot_rad_vs_gpu": W.rotation_error(T, T_gpu), "transl_vs_gpu": float(np.linalg.norm(T[:3, 3] - T_gpu[:3, 3]))}
+
+
 def cpu_reference_step(orc, pair):
     src, tgt, _ = pair
     t0 = time.perf_counter()
@@ -311,6 +335,7 @@ def run_b200(args):
                "parity_vs_gpu": {"rot_rad": W.rotation_error(T_cpu, T_dev[0]),
                                  "transl": float(np.linalg.norm(T_cpu[:3, 3] - T_dev[0][:3, 3])),
                                  "iterations_cpu": st_cpu.num_iterations, "iterations_gpu": stats[0].num_iterations}}
+        cpu["reference_source_build"] = reference_source_build_step(pairs[0], T_dev[0])
     if rank == 0:
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

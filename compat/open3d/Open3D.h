@@ -31,6 +31,14 @@ inline std::mt19937& Engine() {
 }
 inline void Seed(int seed) { Engine().seed((unsigned)seed); }
 }  // namespace random
+typedef std::allocator<Eigen::Vector6d> Vector6d_allocator;
+template <typename... Args>
+inline void LogDebug(const char*, Args&&...) {}
+inline Eigen::Matrix3d SkewMatrix(const Eigen::Vector3d& v) {
+    Eigen::Matrix3d m;
+    m(0, 1) = -v[2], m(0, 2) = v[1], m(1, 0) = v[2], m(1, 2) = -v[0], m(2, 0) = -v[1], m(2, 1) = v[0];
+    return m;
+}
 }  // namespace utility
 
 namespace geometry {
@@ -93,32 +101,37 @@ public:
         for (size_t i : idx) out->points_.push_back(points_[i]);
         return out;
     }
-    // Only the FGR baselines and diagnostics of the reference's drivers call these (out of scope);
-    // the registration path computes its normals on the GPU.
-    void EstimateNormals(const KDTreeSearchParam& = KDTreeSearchParamKNN(), bool = true) {
-        std::cerr << "[compat] open3d::geometry::PointCloud::EstimateNormals is not provided by the stand-in\n";
-    }
+    inline void EstimateNormals(const KDTreeSearchParam& search_param = KDTreeSearchParamKNN(),
+                                bool fast_normal_computation = true);
     inline std::vector<double> ComputePointCloudDistance(const PointCloud& target) const;
     PointCloud& PaintUniformColor(const Eigen::Vector3d&) { return *this; }
 };
 
 // The registration path never searches this tree (its spatial indices live on the GPU); the stand-in is a plain
-// CPU kd-tree so that the reference's evaluation helpers (src/cc.cpp:116-143,220-237) still work.
+// CPU kd-tree of any dimension (SetGeometry: 3-D, SetMatrixData: one point per COLUMN) so that the reference's
+// evaluation helpers (src/cc.cpp:116-143,220-237) work.  Exact search; equal distances resolve to the smallest index.
 class KDTreeFlann {
 public:
     KDTreeFlann() = default;
     explicit KDTreeFlann(const PointCloud& pc) { SetGeometry(pc); }
     bool SetGeometry(const PointCloud& pc) {
-        pts_ = pc.points_;
-        perm_.resize(pts_.size());
-        std::iota(perm_.begin(), perm_.end(), 0);
-        nodes_.clear();
-        if (!pts_.empty()) Build(0, (int)pts_.size());
-        return true;
+        dim_ = 3;
+        data_.resize(pc.points_.size() * 3);
+        for (size_t i = 0; i < pc.points_.size(); i++)
+            for (int d = 0; d < 3; d++) data_[i * 3 + d] = pc.points_[i][d];
+        return Rebuild();
     }
-    int SearchKNN(const Eigen::Vector3d& q, int knn, std::vector<int>& indices, std::vector<double>& distance2) const {
+    bool SetMatrixData(const Eigen::MatrixXd& data) {
+        dim_ = (int)data.rows();
+        data_.assign(data.data(), data.data() + data.size());  // column-major: column i = point i
+        return Rebuild();
+    }
+    template <typename Q>
+    int SearchKNN(const Q& q, int knn, std::vector<int>& indices, std::vector<double>& distance2) const {
         std::vector<std::pair<double, int>> heap;
-        if (!nodes_.empty() && knn > 0) Search(0, q, (size_t)knn, 1e300, heap);
+        double qv[kMaxDim];
+        for (int d = 0; d < dim_; d++) qv[d] = q(d);
+        if (!nodes_.empty() && knn > 0) Search(0, qv, (size_t)knn, 1e300, heap);
         std::sort_heap(heap.begin(), heap.end());
         indices.resize(heap.size());
         distance2.resize(heap.size());
@@ -128,9 +141,12 @@ public:
         }
         return (int)heap.size();
     }
-    int SearchRadius(const Eigen::Vector3d& q, double radius, std::vector<int>& indices, std::vector<double>& distance2) const {
+    template <typename Q>
+    int SearchRadius(const Q& q, double radius, std::vector<int>& indices, std::vector<double>& distance2) const {
         std::vector<std::pair<double, int>> heap;
-        if (!nodes_.empty()) Search(0, q, pts_.size(), radius * radius, heap);
+        double qv[kMaxDim];
+        for (int d = 0; d < dim_; d++) qv[d] = q(d);
+        if (!nodes_.empty()) Search(0, qv, n_points(), radius * radius, heap);
         std::sort_heap(heap.begin(), heap.end());
         indices.clear();
         distance2.clear();
@@ -142,51 +158,66 @@ public:
     }
 
 private:
+    static constexpr int kMaxDim = 16;
     struct Node {
         int left = -1, right = -1, dim = -1, begin = 0, end = 0;
         double split = 0;
     };
-    std::vector<Eigen::Vector3d> pts_;
+    int dim_ = 3;
+    std::vector<double> data_;
     std::vector<int> perm_;
     std::vector<Node> nodes_;
+    size_t n_points() const { return data_.size() / (size_t)dim_; }
+    double at(int i, int d) const { return data_[(size_t)i * dim_ + d]; }
+    bool Rebuild() {
+        if (dim_ < 1 || dim_ > kMaxDim) return false;
+        perm_.resize(n_points());
+        std::iota(perm_.begin(), perm_.end(), 0);
+        nodes_.clear();
+        if (!perm_.empty()) Build(0, (int)perm_.size());
+        return true;
+    }
     int Build(int b, int e) {
         int id = (int)nodes_.size();
         nodes_.emplace_back();
         nodes_[id].begin = b;
         nodes_[id].end = e;
         if (e - b <= 16) return id;
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        for (int i = b; i < e; i++)
-            for (int d = 0; d < 3; d++) {
-                lo[d] = std::min(lo[d], pts_[perm_[i]][d]);
-                hi[d] = std::max(hi[d], pts_[perm_[i]][d]);
-            }
         int dim = 0;
-        for (int d = 1; d < 3; d++)
-            if (hi[d] - lo[d] > hi[dim] - lo[dim]) dim = d;
+        double best = -1.0;
+        for (int d = 0; d < dim_; d++) {
+            double lo = 1e300, hi = -1e300;
+            for (int i = b; i < e; i++) lo = std::min(lo, at(perm_[i], d)), hi = std::max(hi, at(perm_[i], d));
+            if (hi - lo > best) best = hi - lo, dim = d;
+        }
         int mid = (b + e) / 2;
         std::nth_element(perm_.begin() + b, perm_.begin() + mid, perm_.begin() + e,
-                         [&](int x, int y) { return pts_[x][dim] < pts_[y][dim]; });
+                         [&](int x, int y) { return at(x, dim) < at(y, dim); });
         nodes_[id].dim = dim;
-        nodes_[id].split = pts_[perm_[mid]][dim];
+        nodes_[id].split = at(perm_[mid], dim);
         int l = Build(b, mid);
         int r = Build(mid, e);
         nodes_[id].left = l;
         nodes_[id].right = r;
         return id;
     }
-    void Search(int id, const Eigen::Vector3d& q, size_t k, double max_d2, std::vector<std::pair<double, int>>& heap) const {
+    void Search(int id, const double* q, size_t k, double max_d2, std::vector<std::pair<double, int>>& heap) const {
         const Node& nd = nodes_[id];
         if (nd.dim < 0) {
             for (int i = nd.begin; i < nd.end; i++) {
-                double d2 = (pts_[perm_[i]] - q).squaredNorm();
+                double d2 = 0.0;
+                for (int d = 0; d < dim_; d++) {
+                    double t = at(perm_[i], d) - q[d];
+                    d2 += t * t;
+                }
                 if (d2 > max_d2) continue;
+                std::pair<double, int> cand(d2, perm_[i]);
                 if (heap.size() < k) {
-                    heap.emplace_back(d2, perm_[i]);
+                    heap.push_back(cand);
                     std::push_heap(heap.begin(), heap.end());
-                } else if (d2 < heap.front().first) {
+                } else if (cand < heap.front()) {
                     std::pop_heap(heap.begin(), heap.end());
-                    heap.back() = {d2, perm_[i]};
+                    heap.back() = cand;
                     std::push_heap(heap.begin(), heap.end());
                 }
             }
@@ -214,10 +245,24 @@ inline std::vector<double> PointCloud::ComputePointCloudDistance(const PointClou
 namespace pipelines {
 namespace registration {
 typedef std::vector<Eigen::Vector2i> CorrespondenceSet;
-// member types only: the estimators run inside libse3icp_cuda.so
-class TransformationEstimationPointToPoint {};
-class TransformationEstimationPointToPlane {};
-class TransformationEstimationForGeneralizedICP {};
+// Member types of the registration class.  In the product build the estimators run inside libse3icp_cuda.so and
+// ComputeTransformation is declared but never defined or called; the CPU definitions exist only in the oracle's
+// build of the reference source (oracle/refdeps/third_party_numerics.h, -DSE3ICP_REFERENCE_BUILD).
+class TransformationEstimationPointToPoint {
+public:
+    Eigen::Matrix4d ComputeTransformation(const geometry::PointCloud& source, const geometry::PointCloud& target,
+                                          const CorrespondenceSet& corres) const;
+};
+class TransformationEstimationPointToPlane {
+public:
+    Eigen::Matrix4d ComputeTransformation(const geometry::PointCloud& source, const geometry::PointCloud& target,
+                                          const CorrespondenceSet& corres) const;
+};
+class TransformationEstimationForGeneralizedICP {
+public:
+    Eigen::Matrix4d ComputeTransformation(const geometry::PointCloud& source, const geometry::PointCloud& target,
+                                          const CorrespondenceSet& corres) const;
+};
 
 // FPFH + Fast Global Registration are a different algorithm (baseline branches of the reference's drivers,
 // OUT OF SCOPE in SURVEY §2.1).  The stand-ins let those translation units compile; calling them reports it.
@@ -381,3 +426,14 @@ inline bool WritePointCloud(const std::string& filename, const geometry::PointCl
 
 }  // namespace io
 }  // namespace open3d
+
+#ifdef SE3ICP_REFERENCE_BUILD
+// oracle-only: CPU restatements of the third-party numerics the reference source calls (test infrastructure)
+#include "../../oracle/refdeps/third_party_numerics.h"
+#else
+// Only the FGR baselines and diagnostics of the reference's drivers call this (out of scope);
+// the registration path computes its normals on the GPU.
+inline void open3d::geometry::PointCloud::EstimateNormals(const KDTreeSearchParam&, bool) {
+    std::cerr << "[compat] open3d::geometry::PointCloud::EstimateNormals is not provided by the stand-in\n";
+}
+#endif

@@ -1,10 +1,11 @@
 /*
  * se3icp_oracle.cpp — CPU oracle for the SE(3)-ICP registration path.
  *
- * TEST INFRASTRUCTURE ONLY (see se3icp_oracle.h).  PARITY UNPINNED at the
- * Open3D / PCL / Eigen boundaries: those libraries are not vendored in the
- * reference and are absent from this image, so their behaviour is restated here
- * from their published algorithms:
+ * TEST INFRASTRUCTURE ONLY (see se3icp_oracle.h).  Pinned against the
+ * reference's own source through oracle/_ref (tests/test_reference_build.py);
+ * PARITY UNPINNED at the Open3D / PCL / Eigen boundaries: those libraries are
+ * not vendored in the reference and are absent from this image, so their
+ * behaviour is restated here from their published algorithms:
  *   - Open3D 0.19.0 @1868f4332: KDTreeFlann (nanoflann, exact L2 kNN, results
  *     ascending), PointCloud::{GetCenter,Translate,Scale,Transform,
  *     EstimateNormals}, TransformationEstimation{PointToPoint (Eigen::umeyama,

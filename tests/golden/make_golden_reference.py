@@ -1,0 +1,82 @@
+"""Golden results from the REFERENCE'S OWN SOURCE (oracle/_ref/libse3icp_reference.so: the unmodified
+src/iterative_SE3_registration.cpp of /root/reference compiled by oracle/Makefile against compat/ + oracle/refdeps/).
+
+The reference tree does not exist on the GPU box, so its answers travel as this fixture:
+
+    python tests/golden/make_golden_reference.py        # needs /root/reference; ~1 min
+
+Every case is (inputs regenerated from workloads.py by seed, parameters, entry, variant) -> final transform and the
+iteration counters of the reference class.  tests/test_reference_build.py replays them against the oracle (CPU) and
+tests/test_gpu_parity.py against the CUDA path (GPU).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import workloads as W  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+ENTRY_OF = {"icp": "run_icp", "se3": "run_se3_icp", "cf": "run_se3_icp_with_cf", "pure": "run_se3_pure"}
+
+
+def cases():
+    """name -> dict(cloud=(kind, kwargs), entry, variant, params)"""
+    out = {}
+    for e in ("icp", "se3", "pure"):
+        for v in ("pt2pt", "pt2pl", "gicp"):
+            out["c1_%s_%s" % (e, v)] = dict(cloud=("c1", {}), entry=e, variant=v, params={})
+    out["c1_cf"] = dict(cloud=("c1", {}), entry="cf", variant="gicp", params={})
+    out["c1_se3_pt2pl_trim80"] = dict(cloud=("c1", {}), entry="se3", variant="pt2pl", params=dict(estimated_overlap=0.8))
+    out["c1_se3_gicp_trim70_largest"] = dict(cloud=("c1", {}), entry="se3", variant="gicp",
+                                             params=dict(estimated_overlap=0.7, trim_keep_largest=1))
+    out["c1_se3_pt2pt_alpha1_knn60"] = dict(cloud=("c1", {}), entry="se3", variant="pt2pt",
+                                            params=dict(alpha_rot=1.0, beta_transl=2.0, number_of_nn_for_LRF=60,
+                                                        scale_preprocessing=2.0))
+    for level, seed in (("easy", 1), ("moderate", 2)):
+        for v in ("pt2pt", "pt2pl", "gicp"):
+            out["bunny_%s_%s" % (level, v)] = dict(cloud=("bunny", dict(level=level, seed=seed, n_points=3000)), entry="se3",
+                                                   variant=v, params=dict(number_of_nn_for_LRF=90, estimated_overlap=0.9))
+    out["lidar_small_se3_gicp"] = dict(cloud=("lidar", dict(seed=3, n_rings=32, n_az=400)), entry="se3", variant="gicp",
+                                       params=dict(W.KITTI_PARAMS))
+    out["rgbd_small_cf"] = dict(cloud=("rgbd", dict(seed=1, stride=6)), entry="cf", variant="gicp", params=dict(W.LOUNGE_PARAMS))
+    out["kitti_full_se3_gicp"] = dict(cloud=("lidar", dict(seed=0)), entry="se3", variant="gicp", params=dict(W.KITTI_PARAMS))
+    out["lounge_full_cf"] = dict(cloud=("rgbd", dict(seed=0)), entry="cf", variant="gicp", params=dict(W.LOUNGE_PARAMS))
+    return out
+
+
+def load_cloud(kind, kw):
+    if kind == "c1":
+        s, t, _ = W.load_c1()
+    elif kind == "bunny":
+        s, t, _ = W.bunny_problem(**kw)
+    elif kind == "lidar":
+        s, t, _ = W.lidar_pair(**kw)
+    elif kind == "rgbd":
+        s, t, _ = W.rgbd_pair(**kw)
+    else:
+        raise KeyError(kind)
+    return np.ascontiguousarray(s, np.float64), np.ascontiguousarray(t, np.float64)
+
+
+def main():
+    from oracle import reference_build as RB
+    res = {}
+    spec = cases()
+    for name, c in spec.items():
+        s, t = load_cloud(*c["cloud"])
+        T, it, it_se3 = RB.run(ENTRY_OF[c["entry"]], c["variant"], s, t, RB.default_params(**c["params"]))
+        res[name + "/T"] = T
+        res[name + "/it"] = np.array([it, it_se3], np.int32)
+        res[name + "/n"] = np.array([len(s), len(t)], np.int64)
+        print("%-32s n=%d/%d it=%d/%d" % (name, len(s), len(t), it, it_se3), flush=True)
+    np.savez(os.path.join(OUT, "reference_build.npz"), **res)
+    with open(os.path.join(OUT, "reference_build_cases.json"), "w") as f:
+        json.dump(spec, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

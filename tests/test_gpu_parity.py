@@ -483,3 +483,30 @@ def test_coherence_filter_is_exact(ctx, capi, c1, bunny4k, problem):
         np.testing.assert_array_equal(ia, ib)
         np.testing.assert_array_equal(da, db)
         assert (sa.num_iterations, sa.num_pure_se3_iterations) == (sb.num_iterations, sb.num_pure_se3_iterations)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CUDA path against the REFERENCE'S OWN SOURCE: tests/golden/reference_build.npz holds what the unmodified
+# src/iterative_SE3_registration.cpp returns (oracle/Makefile `ref`, tests/golden/make_golden_reference.py).
+import importlib.util  # noqa: E402
+import json  # noqa: E402
+
+_mg_spec = importlib.util.spec_from_file_location("make_golden_reference", os.path.join(W.GOLDEN, "make_golden_reference.py"))
+_MG = importlib.util.module_from_spec(_mg_spec)
+_mg_spec.loader.exec_module(_MG)
+with open(os.path.join(W.GOLDEN, "reference_build_cases.json")) as _f:
+    REF_CASES = json.load(_f)
+REF_ENTRY = {"icp": "RUN_ICP", "se3": "RUN_SE3_ICP", "cf": "RUN_SE3_ICP_CF", "pure": "RUN_SE3_PURE"}
+
+
+@pytest.mark.parametrize("name", sorted(REF_CASES))
+def test_cuda_path_reproduces_reference_source(ctx, capi, name):
+    gold = np.load(os.path.join(W.GOLDEN, "reference_build.npz"))
+    c = REF_CASES[name]
+    src, tgt = _MG.load_cloud(*c["cloud"])
+    assert [len(src), len(tgt)] == list(gold[name + "/n"])
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    Tg, sg = ctx.run(capi.default_params(variant=c["variant"], entry=getattr(capi, REF_ENTRY[c["entry"]]), **c["params"]))
+    assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold[name + "/it"])
+    assert_transform_parity(Tg, gold[name + "/T"], tgt)
