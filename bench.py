@@ -206,7 +206,19 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout when the communicator is created; stdout carries the one
+        # JSON line only, so library chatter goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     pkg = graft.load_package()
     capi = pkg.capi
