@@ -594,7 +594,16 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         set_last_error("no run pending");
         return SE3ICP_ERR_STATE;
     }
-    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->blocking_wait) {
+        // ev_end is the last thing enqueued by run_async.  Poll and yield: as responsive as a spin when cores are free,
+        // and the core goes to a thread that is enqueueing when they are not (8 ranks x 8 contexts on one host)
+        cudaError_t q;
+        while ((q = cudaEventQuery(c->ev_end)) == cudaErrorNotReady) std::this_thread::yield();
+        SE3_CUDA(q);
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+    }
     c->run_pending = false;
     const IterState& hs = *c->h_state;
     if (T_out) memcpy(T_out, hs.T_final, 16 * sizeof(double));
@@ -690,6 +699,9 @@ static int run_batch_impl(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const doubl
     std::vector<std::string> errs(n_ctx);
     auto worker = [&](int ci) {
         se3icp_ctx* c = ctxs[ci];
+        // several host threads per GPU (and one process per GPU next to it): waiting threads yield while they poll
+        // the end event, so the cores stay available to the threads that are enqueueing
+        c->blocking_wait = n_ctx > 1;
         for (int pi = ci; pi < n_pairs; pi += n_ctx) {
             int r;
             if (device_inputs) {
@@ -703,9 +715,10 @@ static int run_batch_impl(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const doubl
             if (r) {
                 rc[ci] = r;
                 errs[ci] = se3icp_last_error();
-                return;
+                break;
             }
         }
+        c->blocking_wait = false;
     };
     if (n_ctx == 1) {
         worker(0);

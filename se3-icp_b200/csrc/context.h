@@ -40,6 +40,7 @@ struct se3icp_ctx {
     se3::RunConfig cfg{};
     se3icp_params params{};
     bool run_pending = false;
+    bool blocking_wait = false;  // run_finish polls ev_end and yields instead of spinning (batches with several host threads)
     bool src_index_built = false;  // index[0].perm holds the source's Morton order of the current run
     cudaGraph_t loop_graph = nullptr;        // WHILE-loop graph of the last run (use_graph)
     cudaGraphExec_t loop_exec = nullptr;
