@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SE3ICP_ABI_VERSION 1
+#define SE3ICP_ABI_VERSION 2
 
 enum se3icp_status {
     SE3ICP_OK = 0,
@@ -82,6 +82,8 @@ typedef struct se3icp_params {
     int32_t use_graph;              /* 1 = capture the iteration in a CUDA graph */
     int32_t record_history;         /* 1 = keep per-iteration T_i (reference estimated_history_, hpp:63) */
     int32_t nn_coherence;           /* 1 = SE(3) search may skip queries whose previous match is provably still nearest */
+    int32_t reuse_features;         /* 1 = keep a cloud's LRFs / normals / covariances across runs while the cloud stays in the
+                                       context (se3icp_swap_clouds, se3icp_run_sequence); 0 = recompute every run */
 } se3icp_params;
 
 typedef struct se3icp_stats {
@@ -95,6 +97,7 @@ typedef struct se3icp_stats {
     int64_t exact_repairs;           /* queries re-done by the exact FP64 repair kernel */
     int64_t kernel_launches;         /* kernels of this library launched during the run */
     double time_se3_phase_search_ms; /* device time of the 12-D correspondence stage, summed over the SE(3) iterations */
+    int64_t feature_reuses;          /* clouds whose neighbourhood features were taken from an earlier run (0, 1 or 2) */
 } se3icp_stats;
 
 typedef struct se3icp_ctx se3icp_ctx;
@@ -137,6 +140,20 @@ int se3icp_run_batch(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const double* co
 int se3icp_run_batch_device(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const double* const* d_src, const size_t* n_src,
                             const double* const* d_tgt, const size_t* n_tgt, const se3icp_params* p, double* T_out,
                             se3icp_stats* stats);
+
+/* Odometry-style sequences (reference examples/benchmark_kitti.cpp:120-131 registers scan i+1 onto scan i, so every
+ * scan is the source of one pair and the target of the next).  se3icp_swap_clouds exchanges the two slots of the
+ * context together with everything derived from them; with params.reuse_features the next run then skips the
+ * kNN-90 / LRF / normal / covariance stage for the cloud that already went through it.  Those features are invariant
+ * under the per-pair normalisation (a uniform scale about the cloud's own centroid, .cpp:568-582), so the result
+ * agrees with an independent run of the pair to rounding (tests: <= 1e-9, equal iteration counts); it is not
+ * bit-identical, because the reference recomputes the neighbourhoods at the new scale.  Extension, not in the reference. */
+int se3icp_swap_clouds(se3icp_ctx* ctx);
+/* registers scans[i+1] (source) onto scans[i] (target) for i = 0 .. n_scans-2, reusing each scan's features once.
+ * scans[i]: n_points[i] x 3 doubles, host buffers (device_inputs = 0) or device buffers that stay valid (1). */
+int se3icp_run_sequence(se3icp_ctx* ctx, const double* const* scans, const size_t* n_points, int n_scans,
+                        const se3icp_params* p, int device_inputs, double* T_out /*[(n_scans-1)*16]*/,
+                        se3icp_stats* stats /*[n_scans-1] or NULL*/);
 
 /* one very large pair (BASELINE.json configs[4]): every rank holds both clouds (se3icp_set_cloud), owns the
  * source query range [src_begin, src_end) for LRF set-up, correspondence search and reduction, and the

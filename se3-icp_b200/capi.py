@@ -50,6 +50,7 @@ class Params(C.Structure):
         ("use_graph", C.c_int32),
         ("record_history", C.c_int32),
         ("nn_coherence", C.c_int32),
+        ("reuse_features", C.c_int32),
     ]
 
 
@@ -65,6 +66,7 @@ class Stats(C.Structure):
         ("exact_repairs", C.c_int64),
         ("kernel_launches", C.c_int64),
         ("time_se3_phase_search_ms", C.c_double),
+        ("feature_reuses", C.c_int64),
     ]
 
 
@@ -72,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "se3icp_abi_version", "se3icp_last_error", "se3icp_default_params", "se3icp_create", "se3icp_destroy",
     "se3icp_synchronize", "se3icp_set_cloud", "se3icp_set_cloud_device", "se3icp_run", "se3icp_run_async",
     "se3icp_run_finish", "se3icp_get_history", "se3icp_get_correspondences", "se3icp_get_se3_cloud",
-    "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_run_sharded", "se3icp_comm_unique_id", "se3icp_comm_init",
+    "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_swap_clouds", "se3icp_run_sequence", "se3icp_run_sharded", "se3icp_comm_unique_id", "se3icp_comm_init",
     "se3icp_comm_destroy", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
     "se3icp_normals", "se3icp_gicp_cov", "se3icp_nn_se3", "se3icp_nn_xyz", "se3icp_trim", "se3icp_reduce_pt2pt",
     "se3icp_reduce_pt2pl", "se3icp_reduce_gicp", "se3icp_solve",
@@ -187,6 +189,31 @@ class Context:
     def set_cloud_device(self, which, dev_ptr, n):
         _check(lib().se3icp_set_cloud_device(self._h, int(which), C.c_void_p(int(dev_ptr)), C.c_size_t(n)))
         self.n[which] = n
+
+    def swap_clouds(self):
+        """source <-> target together with their indices and neighbourhood features (se3icp_swap_clouds)"""
+        _check(lib().se3icp_swap_clouds(self._h))
+        self.n[SOURCE], self.n[TARGET] = self.n[TARGET], self.n[SOURCE]
+
+    def run_sequence(self, scans, params, device_inputs=False):
+        """Registers scans[i+1] onto scans[i] for consecutive scans, computing each scan's features once.
+        scans: list of (n, 3) arrays (host) or (device_ptr, n) tuples.  Returns (T [n-1, 4, 4], [Stats])."""
+        m = len(scans)
+        ptr = (C.c_void_p * m)()
+        cnt = (C.c_size_t * m)()
+        keep = []
+        for i, sc in enumerate(scans):
+            if device_inputs:
+                ptr[i], cnt[i] = int(sc[0]), int(sc[1])
+            else:
+                a = _f64(sc)
+                keep.append(a)
+                ptr[i], cnt[i] = a.ctypes.data, a.shape[0]
+        T = np.zeros((m - 1, 4, 4))
+        stats = (Stats * (m - 1))()
+        _check(lib().se3icp_run_sequence(self._h, ptr, cnt, m, C.byref(params), int(bool(device_inputs)), _dp(T), stats))
+        self.n[SOURCE], self.n[TARGET] = int(cnt[m - 1]), int(cnt[m - 2])
+        return T, list(stats)
 
     def run(self, params):
         T = np.zeros((4, 4))

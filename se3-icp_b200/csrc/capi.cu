@@ -276,8 +276,20 @@ int enqueue_setup(se3icp_ctx* c) {
             fa.q_end = c->shard_end;
         }
         if (fa.K <= 0) continue;
+        se3icp_ctx::FeatureKey key;
+        key.valid = !(w == 0 && c->sharded);  // a sharded source only holds its own range
+        key.n = c->n[w];
+        key.k_lrf = fa.k_lrf, key.k_nrm = fa.k_nrm, key.want_cov = fa.want_cov, key.eps = fa.gicp_eps;
+        const se3icp_ctx::FeatureKey& have = c->feat[w];
+        if (p.reuse_features && have.valid && key.valid && have.n == key.n && have.k_lrf == key.k_lrf &&
+            have.k_nrm == key.k_nrm && have.want_cov == key.want_cov && have.eps == key.eps) {
+            c->feature_reuses += 1;  // computed by an earlier run on this very cloud (se3icp_swap_clouds)
+            continue;
+        }
+        c->feat[w].valid = false;
         SE3_TRY(launch_knn_features(c->index[w].view, fa, st));
         c->launches += 1;
+        c->feat[w] = key;
     }
     if (cfg.has_se3)  // .cpp:597-626: weighting, 12 x M matrix and its search structure
         SE3_TRY(c->se3idx.build(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.with_cf ? 1.0 : cfg.beta, ds, st,
@@ -417,6 +429,7 @@ void se3icp_default_params(se3icp_params* p) {  // reference ctor .cpp:334-348
     p->use_graph = 1;  /* whole loop as one CUDA graph (conditional WHILE node) */
     p->record_history = 0;
     p->nn_coherence = 1;
+    p->reuse_features = 1;
 }
 
 int se3icp_create(int device, void* stream, se3icp_ctx** out) {
@@ -499,6 +512,7 @@ int se3icp_set_cloud(se3icp_ctx* c, int which, const double* xyz, size_t n, int 
                                  c->stream));
     c->raw_view[which] = c->raw[which].as<double>();
     c->n[which] = total;
+    c->feat[which].valid = false;
     return SE3ICP_OK;
 }
 
@@ -507,6 +521,28 @@ int se3icp_set_cloud_device(se3icp_ctx* c, int which, const double* d_xyz, size_
     if ((which != SE3ICP_SOURCE && which != SE3ICP_TARGET) || !d_xyz || n == 0) return SE3ICP_ERR_ARG;
     c->raw_view[which] = d_xyz;
     c->n[which] = n;
+    c->feat[which].valid = false;
+    return SE3ICP_OK;
+}
+
+int se3icp_swap_clouds(se3icp_ctx* c) {
+    SE3_TRY(check_ctx(c));
+    if (c->run_pending) {
+        set_last_error("se3icp_swap_clouds: a run is pending");
+        return SE3ICP_ERR_STATE;
+    }
+    c->raw[0].swap(c->raw[1]);
+    std::swap(c->raw_view[0], c->raw_view[1]);
+    std::swap(c->n[0], c->n[1]);
+    c->index[0].swap(c->index[1]);
+    c->frame[0].swap(c->frame[1]);
+    c->nrm[0].swap(c->nrm[1]);
+    c->cov[0].swap(c->cov[1]);
+    c->conf[0].swap(c->conf[1]);
+    c->psum[0].swap(c->psum[1]);
+    c->pmax[0].swap(c->pmax[1]);
+    std::swap(c->feat[0], c->feat[1]);
+    c->src_index_built = false;
     return SE3ICP_OK;
 }
 
@@ -536,6 +572,7 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     SE3_TRY(fill_config(c, p));
     SE3_TRY(alloc_run(c));
     c->launches = 0;
+    c->feature_reuses = 0;
     SE3_CUDA(cudaEventRecord(c->ev_begin, c->stream));
     SE3_TRY(enqueue_setup(c));
     SE3_CUDA(cudaEventRecord(c->ev_setup, c->stream));
@@ -622,6 +659,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         stats->time_before_pure_icp_ms = stats->time_total_ms;  // .cpp:957-958 measures the whole call
         stats->exact_repairs = hs.total_repairs;
         stats->kernel_launches = c->launches + (c->graph_run ? c->launches_per_iter * (long long)hs.iter : 0);
+        stats->feature_reuses = c->feature_reuses;
     }
     return SE3ICP_OK;
 }
@@ -732,6 +770,23 @@ static int run_batch_impl(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const doubl
             set_last_error("%s", errs[ci].c_str());
             return rc[ci];
         }
+    return SE3ICP_OK;
+}
+
+int se3icp_run_sequence(se3icp_ctx* c, const double* const* scans, const size_t* n_points, int n_scans,
+                        const se3icp_params* p, int device_inputs, double* T_out, se3icp_stats* stats) {
+    SE3_TRY(check_ctx(c));
+    if (!scans || !n_points || n_scans < 2 || !p || !T_out) return SE3ICP_ERR_ARG;
+    auto load = [&](int which, int i) {
+        return device_inputs ? se3icp_set_cloud_device(c, which, scans[i], n_points[i])
+                             : se3icp_set_cloud(c, which, scans[i], n_points[i], 0);
+    };
+    SE3_TRY(load(SE3ICP_SOURCE, 0));
+    for (int i = 0; i + 1 < n_scans; i++) {
+        SE3_TRY(se3icp_swap_clouds(c));  // scan i, source of the previous pair (features kept), becomes the target
+        SE3_TRY(load(SE3ICP_SOURCE, i + 1));
+        SE3_TRY(se3icp_run(c, p, T_out + 16 * (size_t)i, stats ? stats + i : nullptr));
+    }
     return SE3ICP_OK;
 }
 

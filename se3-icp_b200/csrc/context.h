@@ -33,6 +33,17 @@ struct se3icp_ctx {
     bool sharded = false;
     int shard_begin = 0, shard_end = 0;
 
+    // What frame[w] / nrm[w] / cov[w] currently hold: the neighbourhood features of the cloud in slot w are invariant
+    // under the per-pair normalisation (uniform scale about the cloud's own centroid), so a scan that was the source of
+    // one pair can serve as the target of the next without recomputing them (se3icp_swap_clouds).
+    struct FeatureKey {
+        bool valid = false;
+        size_t n = 0;
+        int k_lrf = 0, k_nrm = 0, want_cov = 0;
+        double eps = 0.0;
+    } feat[2];
+    long long feature_reuses = 0;
+
     se3::IterState* h_state = nullptr;  // pinned
     int* h_flag = nullptr;              // pinned
     cudaEvent_t ev_begin = nullptr, ev_setup = nullptr, ev_end = nullptr;

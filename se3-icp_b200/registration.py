@@ -140,3 +140,21 @@ def run_registration_method(method, source, target, **fields):
     else:
         raise ValueError("Not a valid algorithm name; available: %s" % ", ".join(METHODS))
     return reg
+
+
+def register_sequence(method, scans, device=0, **params):
+    """Odometry-style driver (examples/benchmark_kitti.cpp:120-131): registers scans[i+1] onto scans[i] for every
+    consecutive pair on one GPU context, computing each scan's neighbourhood features once (se3icp_run_sequence;
+    extension of the reference API).  method: "se3_pt2pt" | "se3_pt2pl" | "se3_gicp" | "se3_gicp_with_cf" or a plain
+    ICP name; params: fields of se3icp_params (e.g. the KITTI values of benchmark_kitti.cpp:133-148).
+    Returns (T [n-1, 4, 4], [Stats])."""
+    if method in ("pt2pt", "pt2pl", "gicp"):
+        entry, variant = capi.RUN_ICP, method
+    elif method in ("se3_pt2pt", "se3_pt2pl", "se3_gicp"):
+        entry, variant = capi.RUN_SE3_ICP, method[4:]
+    elif method == "se3_gicp_with_cf":
+        entry, variant = capi.RUN_SE3_ICP_CF, "gicp"
+    else:
+        raise ValueError("Not a valid algorithm name; available: %s" % ", ".join(METHODS))
+    ctx = capi.Context(device)
+    return ctx.run_sequence(list(scans), capi.default_params(variant=variant, entry=entry, **params))

@@ -510,3 +510,44 @@ def test_cuda_path_reproduces_reference_source(ctx, capi, name):
     Tg, sg = ctx.run(capi.default_params(variant=c["variant"], entry=getattr(capi, REF_ENTRY[c["entry"]]), **c["params"]))
     assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold[name + "/it"])
     assert_transform_parity(Tg, gold[name + "/T"], tgt)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sequence driver: every scan goes through the kNN-90 / LRF / normal stage once.
+@pytest.mark.parametrize("variant", ["gicp", "pt2pt", "pt2pl"])
+def test_sequence_reuses_features_and_matches_independent_pairs(ctx, capi, variant):
+    scans, steps = W.lidar_sequence(seed=1, n_scans=4, n_rings=32, n_az=500)
+    p = capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, **W.KITTI_PARAMS)
+    T_seq, st_seq = ctx.run_sequence(scans, p)
+    assert [s.feature_reuses for s in st_seq] == ([0, 1, 1] if variant != "pt2pl" else [0, 0, 0])  # pt2pl: target-only normals
+    for i in range(3):
+        ctx.set_cloud(capi.SOURCE, scans[i + 1])
+        ctx.set_cloud(capi.TARGET, scans[i])
+        T_ind, st_ind = ctx.run(p)
+        assert st_ind.feature_reuses == 0
+        assert (st_seq[i].num_iterations, st_seq[i].num_pure_se3_iterations) == (st_ind.num_iterations, st_ind.num_pure_se3_iterations)
+        np.testing.assert_allclose(T_seq[i], T_ind, rtol=0, atol=1e-9)
+        assert rot_err(T_seq[i], steps[i]) < np.radians(0.5)
+    # the switch: no reuse when asked not to, and a run on unchanged clouds may reuse both
+    p_off = capi.default_params(variant=variant, entry=capi.RUN_SE3_ICP, reuse_features=0, **W.KITTI_PARAMS)
+    assert all(s.feature_reuses == 0 for s in ctx.run_sequence(scans, p_off)[1])
+    if variant == "gicp":
+        T_again, st_again = ctx.run(p)
+        T_first, _ = ctx.run(p_off)
+        assert st_again.feature_reuses == 2
+        np.testing.assert_array_equal(T_again, T_first)
+
+
+def test_swap_clouds_registers_the_inverse_problem(ctx, capi, c1):
+    src, tgt, T_gt = c1
+    p = capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM)
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    T_fwd, _ = ctx.run(p)
+    ctx.swap_clouds()
+    T_bwd, st = ctx.run(p)
+    assert rot_err(T_bwd, np.linalg.inv(T_gt)) < 1e-4 and rot_err(T_fwd, T_gt) < 1e-4
+    ctx.set_cloud(capi.SOURCE, tgt)
+    ctx.set_cloud(capi.TARGET, src)
+    T_ref, _ = ctx.run(p)
+    np.testing.assert_allclose(T_bwd, T_ref, rtol=0, atol=1e-9)

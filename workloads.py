@@ -160,6 +160,24 @@ def lidar_pair(seed=0, n_rings=64, n_az=1900, max_range=80.0, sigma=0.02):
     return src, tgt, step  # p_0 = step * p_1
 
 
+def lidar_sequence(seed=0, n_scans=4, n_rings=64, n_az=1900, max_range=80.0, sigma=0.02):
+    """n_scans consecutive scans of one static street scene along a gently curving drive (the shape of KITTI
+    odometry: benchmark_kitti.cpp:120-131 registers scan i+1 onto scan i).  Returns (scans, steps) with
+    steps[i] * scans[i+1] ~ scans[i]."""
+    rng = np.random.default_rng(4000 + seed)
+    boxes, cyl = _street_scene(rng)
+    pose = make_T(rot_3d(0, 0, rng.uniform(-0.05, 0.05)), [rng.uniform(-20, -10), rng.uniform(-1, 1), 0.0])
+    scans, steps = [], []
+    for k in range(n_scans):
+        scans.append(_lidar_scan(pose, boxes, cyl, rng, n_rings, n_az, max_range, sigma))
+        step = make_T(rot_3d(rng.uniform(-0.005, 0.005), rng.uniform(-0.005, 0.005), np.deg2rad(rng.uniform(-3, 3))),
+                      [rng.uniform(1.0, 1.5), rng.uniform(-0.05, 0.05), rng.uniform(-0.02, 0.02)])
+        if k + 1 < n_scans:
+            steps.append(step)
+        pose = pose @ step
+    return scans, steps
+
+
 KITTI_PARAMS = dict(estimated_overlap=0.7, mse=1e-7, mse_switch_error=5e-7, max_num_se3_iterations=10,
                     number_of_nn_for_LRF=90, alpha_rot=3.0)  # benchmark_kitti.cpp:133-148
 
