@@ -16,9 +16,10 @@ src, tgt, T_gt = W.lidar_pair(seed=0)
 ctx = capi.Context(0)
 ctx.set_cloud(capi.SOURCE, src)
 ctx.set_cloud(capi.TARGET, tgt)
-p = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, **W.KITTI_PARAMS)
+p = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, reuse_features=0, **W.KITTI_PARAMS)  # every run is a full run
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
     T, st = ctx.run(p)
 print("pair: %d/%d points, %d iterations (%d SE3), %.2f ms total, %.2f ms setup, %d launches, rot err %.2e rad" %
       (len(src), len(tgt), st.num_iterations, st.num_pure_se3_iterations, st.time_total_ms, st.time_setup_ms,
        st.kernel_launches, W.rotation_error(T, T_gt)))
+print("SE(3)-phase search %.3f ms, correspondence stage total %.3f ms" % (st.time_se3_phase_search_ms, st.time_se3_correspondence_search_ms))

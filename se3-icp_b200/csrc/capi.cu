@@ -297,6 +297,8 @@ int enqueue_setup(se3icp_ctx* c) {
     SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, (size_t)N * sizeof(int), st));
     if (cfg.coherence || cfg.coherence_xyz) SE3_CUDA(cudaMemsetAsync(c->ref_d2nd.ptr, 0xff, (size_t)N * sizeof(double), st));  // NaN: not known
     if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
+    SE3_TRY(launch_mark_loop_start(ds, st));
+    c->launches += 1;
     return 0;
 }
 

@@ -199,5 +199,6 @@ int launch_solve_update(const RunConfig& cfg, IterState* state, const double* pa
 int launch_loop_condition(unsigned long long cond_handle, const IterState* state, cudaStream_t st);
 int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st);
 int launch_init_state(IterState* state, unsigned int* hist, cudaStream_t st);
+int launch_mark_loop_start(IterState* state, cudaStream_t st);
 
 }  // namespace se3

@@ -64,7 +64,6 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->hist_count = 0;
         st->switch_iter = -1;
         st->work_count = 0;
-    st->corr_stamped = 0;
         st->corr_stamped = 0;
         st->total_repairs = 0;
         st->t_corr_ns = 0;
@@ -759,6 +758,17 @@ int launch_loop_condition(unsigned long long handle, const IterState* state, cud
 
 int launch_finalize(const RunConfig& cfg, IterState* state, cudaStream_t st) {
     finalize_kernel<<<1, 32, 0, st>>>(cfg, state);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// end of the set-up stage: the correspondence timers of the first iteration start here, not at the start of the run
+__global__ void mark_loop_start_kernel(IterState* st) {
+    if (threadIdx.x == 0) st->t_mark = global_timer_ns();
+}
+
+int launch_mark_loop_start(IterState* state, cudaStream_t st) {
+    mark_loop_start_kernel<<<1, 32, 0, st>>>(state);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }
