@@ -7,6 +7,11 @@
 
 namespace se3 {
 
+#ifndef SE3_KEY_LEAD
+#define SE3_KEY_LEAD 2
+#endif
+constexpr int kSe3KeyLead = SE3_KEY_LEAD;
+
 // R in 12-vector order: R[3*c + r] = entry (r, c)
 __device__ __forceinline__ void quat_from_columns(const double* R, double q[4]) {
     double r00 = R[0], r10 = R[1], r20 = R[2], r01 = R[3], r11 = R[4], r21 = R[5], r02 = R[6], r12 = R[7], r22 = R[8];
@@ -66,19 +71,23 @@ __device__ __forceinline__ uint64_t se3_key(const double* R, double px, double p
     c[4] = quant10(py, bbox[1], inv);
     c[5] = quant10(pz, bbox[2], inv);
     uint64_t key = 0;
-    // two leading rotation-only levels
+    // kSe3KeyLead leading rotation-only levels, then rotation bit b interleaved with position bit b + kSe3KeyLead
+    // (all 60 bits are used: the position bits left over at the end follow on their own)
 #pragma unroll
-    for (int b = 9; b >= 8; b--)
-#pragma unroll
-        for (int d = 0; d < 3; d++) key = (key << 1) | ((c[d] >> b) & 1u);
-    // then rotation bit b interleaved with position bit b+2
-#pragma unroll
-    for (int b = 7; b >= 0; b--) {
+    for (int b = 9; b > 9 - kSe3KeyLead; b--)
 #pragma unroll
         for (int d = 0; d < 3; d++) key = (key << 1) | ((c[d] >> b) & 1u);
 #pragma unroll
-        for (int d = 3; d < 6; d++) key = (key << 1) | ((c[d] >> (b + 2)) & 1u);
+    for (int b = 9 - kSe3KeyLead; b >= 0; b--) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) key = (key << 1) | ((c[d] >> b) & 1u);
+#pragma unroll
+        for (int d = 3; d < 6; d++) key = (key << 1) | ((c[d] >> (b + kSe3KeyLead)) & 1u);
     }
+#pragma unroll
+    for (int b = kSe3KeyLead - 1; b >= 0; b--)
+#pragma unroll
+        for (int d = 3; d < 6; d++) key = (key << 1) | ((c[d] >> b) & 1u);
     return key;
 }
 
