@@ -275,13 +275,23 @@ int enqueue_setup(se3icp_ctx* c) {
             fa.q_begin = c->shard_begin;
             fa.q_end = c->shard_end;
         }
+        // sharded pair: every rank needs ALL target features, but each computes only its slice of them; the slices
+        // are exchanged below (one grouped NCCL broadcast per owner and plane, in place)
+        const bool split_target = w == 1 && c->sharded && c->comm && c->comm_size > 1;
+        auto slice = [&](int r, int& b, int& e) {
+            int base = M / c->comm_size, rem = M % c->comm_size;
+            b = r * base + (r < rem ? r : rem);
+            e = b + base + (r < rem ? 1 : 0);
+        };
+        if (split_target) slice(c->comm_rank, fa.q_begin, fa.q_end);
         if (fa.K <= 0) continue;
         se3icp_ctx::FeatureKey key;
         key.valid = !(w == 0 && c->sharded);  // a sharded source only holds its own range
         key.n = c->n[w];
         key.k_lrf = fa.k_lrf, key.k_nrm = fa.k_nrm, key.want_cov = fa.want_cov, key.eps = fa.gicp_eps;
         const se3icp_ctx::FeatureKey& have = c->feat[w];
-        if (p.reuse_features && have.valid && key.valid && have.n == key.n && have.k_lrf == key.k_lrf &&
+        // (never in a multi-rank run: every rank must take part in the exchange below)
+        if (p.reuse_features && !split_target && have.valid && key.valid && have.n == key.n && have.k_lrf == key.k_lrf &&
             have.k_nrm == key.k_nrm && have.want_cov == key.want_cov && have.eps == key.eps) {
             c->feature_reuses += 1;  // computed by an earlier run on this very cloud (se3icp_swap_clouds)
             continue;
@@ -289,6 +299,28 @@ int enqueue_setup(se3icp_ctx* c) {
         c->feat[w].valid = false;
         SE3_TRY(launch_knn_features(c->index[w].view, fa, st));
         c->launches += 1;
+        if (split_target) {
+            const NcclApi* nccl = nccl_api();
+            if (!nccl) return SE3ICP_ERR_NCCL;
+            ncclComm_t comm = (ncclComm_t)c->comm;
+            struct Planes { double* base; int count; } sets[3] = {
+                {fa.k_lrf > 0 ? fa.frame : nullptr, 9}, {fa.k_nrm > 0 ? fa.nrm : nullptr, 3},
+                {fa.k_nrm > 0 && fa.want_cov ? fa.cov : nullptr, 6}};
+            SE3_NCCL(nccl->GroupStart());
+            for (int r = 0; r < c->comm_size; r++) {
+                int b, e;
+                slice(r, b, e);
+                if (e <= b) continue;
+                for (const Planes& ps : sets) {
+                    if (!ps.base) continue;
+                    for (int k = 0; k < ps.count; k++) {
+                        double* ptr = ps.base + (size_t)k * (size_t)M + b;
+                        SE3_NCCL(nccl->Broadcast(ptr, ptr, (size_t)(e - b), ncclDouble, r, comm, st));
+                    }
+                }
+            }
+            SE3_NCCL(nccl->GroupEnd());
+        }
         c->feat[w] = key;
     }
     if (cfg.has_se3)  // .cpp:597-626: weighting, 12 x M matrix and its search structure

@@ -22,8 +22,12 @@ const NcclApi* nccl_api() {
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
         api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
         api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+        api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast &&
+                 api.GroupStart && api.GroupEnd && api.GetErrorString;
     });
     if (!api.ok) {
         set_last_error("libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "symbols missing");
