@@ -28,6 +28,7 @@ struct CloudIndex {
     int n = 0;
     int n_levels = 0;
     int total_nodes = 0;
+    int start_level = 0;  // where traversals begin (see IndexStorage::plan_levels)
     int level_off[kMaxLevels] = {0};
     int level_cnt[kMaxLevels] = {0};
     const double* x = nullptr;
@@ -36,7 +37,8 @@ struct CloudIndex {
     const double* sx = nullptr;
     const double* sy = nullptr;
     const double* sz = nullptr;
-    const int* perm = nullptr;
+    const int* perm = nullptr;      // Morton position -> original index
+    const int* inv = nullptr;       // original index -> Morton position
     const uint64_t* keys = nullptr;
     const float* box = nullptr;     // [6][total_nodes]
     const double* bbox = nullptr;   // device: lo[3], hi[3] of the cloud (for Morton quantisation)

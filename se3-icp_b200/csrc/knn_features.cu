@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
     if (active) {
         for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
         shrink_pool();
-        traverse_boxes(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
+        traverse_boxes<false>(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
             if (leaf >= w0 && leaf <= w1) return;
             eval_leaf(leaf);
         });

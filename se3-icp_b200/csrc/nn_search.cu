@@ -487,7 +487,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
         skip_leaf = first;
     }
     // prune against the second-best bound when it is being tracked
-    traverse_nodes(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
+    traverse_nodes<true>(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
     if (lane == 0) {
         write_se3_match(T, cfg, cb, i, q, best_j, tau);
         if (cfg.coherence) {
@@ -571,21 +571,28 @@ __device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& 
         tau = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
         best = prev;
     }
-    // ... plus, whenever a runner-up is needed or the previous match may be far (cold start, first iteration
-    // after the SE(3) phase), the leaf holding the query's own Morton code
+    // ... plus one whole leaf whenever a runner-up is needed: the previous match's own leaf (one load), or, when
+    // there is no previous match or it may be far (cold start, first iteration after the SE(3) phase), the leaf
+    // holding the query's own Morton code (a binary search: ~17 dependent loads, paid once per run)
     const bool after_switch = cfg.has_se3 && state->iter == state->switch_iter;
     if (coherent || !have_prev || after_switch) {
-        uint64_t key = morton63(qx, qy, qz, I.bbox);
-        int lo = 0, hi = I.n;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (I.keys[mid] < key) lo = mid + 1; else hi = mid;
+        int first;
+        if (have_prev && !after_switch) {
+            first = I.inv[prev] >> 5;
+        } else {
+            uint64_t key = morton63(qx, qy, qz, I.bbox);
+            int lo = 0, hi = I.n;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (I.keys[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= I.n) lo = I.n - 1;
+            first = lo >> 5;
         }
-        if (lo >= I.n) lo = I.n - 1;
-        leaf_fn(lo >> 5);
-        skip_leaf = lo >> 5;
+        leaf_fn(first);
+        skip_leaf = first;
     }
-    traverse_boxes(I, qx, qy, qz, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
+    traverse_boxes<true>(I, qx, qy, qz, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
 
     if (lane == 0) {
         double d = sqrt(tau);  // .cpp:411

@@ -235,9 +235,10 @@ __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ 
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                              const double* __restrict__ z, const int* __restrict__ perm, int n,
                                                              double* __restrict__ sx, double* __restrict__ sy,
-                                                             double* __restrict__ sz) {
+                                                             double* __restrict__ sz, int* __restrict__ inv) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         int o = perm[s];
+        inv[o] = s;  // Morton position of an original index (the sort's value input is dead by now and holds it)
         sx[s] = x[o];
         sy[s] = y[o];
         sz[s] = z[o];
@@ -305,6 +306,17 @@ void IndexStorage::plan_levels(int n) {
     }
     view.n_levels = lvl;
     view.total_nodes = off;
+    // Traversals start at the lowest level that is still small enough to be tested whole (a few independent rounds of
+    // 32 boxes) instead of walking down from the root one dependent expansion at a time; the bound keeps the initial
+    // pushes plus 31 per level below inside the traversal stack (kStackEntries = 192).
+    view.start_level = lvl - 1;
+    for (int l = 0; l < lvl; l++) {
+        int cap = 191 - 31 * l;
+        if (view.level_cnt[l] <= (cap < 128 ? cap : 128)) {
+            view.start_level = l;
+            break;
+        }
+    }
 }
 
 int IndexStorage::reserve(int n) {
@@ -328,6 +340,7 @@ int IndexStorage::reserve(int n) {
                                     (int*)nullptr, n, 0, 63);
     SE3_TRY(sort_tmp.ensure(tmp_bytes + 16));
     sort_tmp_bytes = tmp_bytes;
+    view.inv = vals_tmp.as<int>();
     view.x = x.as<double>();
     view.y = y.as<double>();
     view.z = z.as<double>();
@@ -356,7 +369,7 @@ int IndexStorage::build(cudaStream_t st, long long* launches) {
     SE3_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.ptr, tb, keys_tmp.as<uint64_t>(), keys.as<uint64_t>(),
                                              vals_tmp.as<int>(), perm.as<int>(), n, 0, 63, st));
     gather_sorted_kernel<<<g, 256, 0, st>>>(x.as<double>(), y.as<double>(), z.as<double>(), perm.as<int>(), n,
-                                             sx.as<double>(), sy.as<double>(), sz.as<double>());
+                                             sx.as<double>(), sy.as<double>(), sz.as<double>(), vals_tmp.as<int>());
     int n_leaves = view.level_cnt[0];
     leaf_box_kernel<<<(n_leaves * 32 + 255) / 256, 256, 0, st>>>(sx.as<double>(), sy.as<double>(), sz.as<double>(), n,
                                                                  n_leaves, view.total_nodes, box.as<float>());

@@ -25,23 +25,30 @@ __device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node,
 // `tau` is read on every test, so the leaf functor may shrink it while the traversal runs.
 // lb_fn(node) returns a lower bound of the squared distance from the query to anything below the
 // node; leaf_fn(leaf_id) is called by the whole warp (convergent).
-template <class LbFn, class LeafFn>
+// kWideStart: begin at CloudIndex::start_level (all of its nodes, a few independent rounds) instead of the root level.
+// Pays when the first radius is loose and the upper boxes rarely prune (1-NN searches: -3 %); the kNN search, whose
+// seeded radius prunes whole top-level subtrees, keeps the root start (+2 % otherwise).
+template <bool kWideStart, class LbFn, class LeafFn>
 __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn, const double& tau, int2* stack, int lane,
                                                LeafFn&& leaf_fn) {
     const double kSlack = 1.0 - 1e-12;  // never prune on a rounding-level difference
     int sp = 0;
     {
-        int top = I.n_levels - 1;
-        int cnt = I.level_cnt[top];
-        double lb = 0.0;
-        bool ok = false;
-        if (lane < cnt) {
-            lb = lb_fn(I.level_off[top] + lane);
-            ok = lb * kSlack <= tau;
+        // every node of the start level, 32 at a time: the rounds are independent, so their loads overlap
+        const int top = kWideStart ? I.start_level : I.n_levels - 1;
+        const int cnt = I.level_cnt[top];
+        for (int base = 0; base < cnt; base += 32) {
+            int c = base + lane;
+            double lb = 0.0;
+            bool ok = false;
+            if (c < cnt) {
+                lb = lb_fn(I.level_off[top] + c);
+                ok = lb * kSlack <= tau;
+            }
+            unsigned m = __ballot_sync(SE3_FULL, ok);
+            if (ok) stack[sp + __popc(m & ((1u << lane) - 1u))] = make_int2((top << 27) | c, __float_as_int(__double2float_rd(lb)));
+            sp += __popc(m);
         }
-        unsigned m = __ballot_sync(SE3_FULL, ok);
-        if (ok) stack[sp + __popc(m & ((1u << lane) - 1u))] = make_int2((top << 27) | lane, __float_as_int(__double2float_rd(lb)));
-        sp += __popc(m);
         __syncwarp();
     }
     while (sp > 0) {
@@ -69,10 +76,10 @@ __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn
     }
 }
 
-template <class LeafFn>
+template <bool kWideStart, class LeafFn>
 __device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, double qy, double qz, const double& tau,
                                                int2* stack, int lane, LeafFn&& leaf_fn) {
-    traverse_nodes(I, [&](int node) { return box_lower_bound(I, node, qx, qy, qz); }, tau, stack, lane, leaf_fn);
+    traverse_nodes<kWideStart>(I, [&](int node) { return box_lower_bound(I, node, qx, qy, qz); }, tau, stack, lane, leaf_fn);
 }
 
 }  // namespace se3
