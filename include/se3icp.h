@@ -98,6 +98,8 @@ typedef struct se3icp_stats {
     int64_t kernel_launches;         /* kernels of this library launched during the run */
     double time_se3_phase_search_ms; /* device time of the 12-D correspondence stage, summed over the SE(3) iterations */
     int64_t feature_reuses;          /* clouds whose neighbourhood features were taken from an earlier run (0, 1 or 2) */
+    int64_t queries_searched;        /* nearest-neighbour queries that ran a tree search, summed over the iterations; the
+                                        rest (iterations x source points - this) were settled by the coherence filter */
 } se3icp_stats;
 
 typedef struct se3icp_ctx se3icp_ctx;

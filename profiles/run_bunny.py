@@ -18,3 +18,4 @@ for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 1):
 print("bunny %s se3_%s: %d iterations (%d SE3), %.2f ms total, %.2f ms setup, %d launches, corr stage %.2f ms" %
       (level, variant, st.num_iterations, st.num_pure_se3_iterations, st.time_total_ms, st.time_setup_ms, st.kernel_launches,
        st.time_se3_correspondence_search_ms))
+print("queries searched: %d of %d (%.1f %%)" % (st.queries_searched, st.num_iterations * len(src), 100.0 * st.queries_searched / (st.num_iterations * len(src))))

@@ -23,3 +23,4 @@ print("pair: %d/%d points, %d iterations (%d SE3), %.2f ms total, %.2f ms setup,
       (len(src), len(tgt), st.num_iterations, st.num_pure_se3_iterations, st.time_total_ms, st.time_setup_ms,
        st.kernel_launches, W.rotation_error(T, T_gt)))
 print("SE(3)-phase search %.3f ms, correspondence stage total %.3f ms" % (st.time_se3_phase_search_ms, st.time_se3_correspondence_search_ms))
+print("queries searched: %d of %d (%.1f %%)" % (st.queries_searched, st.num_iterations * len(src), 100.0 * st.queries_searched / (st.num_iterations * len(src))))

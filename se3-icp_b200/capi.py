@@ -67,6 +67,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("time_se3_phase_search_ms", C.c_double),
         ("feature_reuses", C.c_int64),
+        ("queries_searched", C.c_int64),
     ]
 
 

@@ -694,6 +694,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         stats->exact_repairs = hs.total_repairs;
         stats->kernel_launches = c->launches + (c->graph_run ? c->launches_per_iter * (long long)hs.iter : 0);
         stats->feature_reuses = c->feature_reuses;
+        stats->queries_searched = (long long)hs.searched_total;
     }
     return SE3ICP_OK;
 }

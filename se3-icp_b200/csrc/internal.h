@@ -67,6 +67,7 @@ struct IterState {
     int switch_iter;  // value of iter when the ICP phase began (-1 before)
     int work_count;   // entries of the coherence work list (reset every iteration)
     int corr_stamped; // the end of this iteration's correspondence stage has been time-stamped
+    unsigned long long searched_total;  // queries the coherence filter could NOT settle, summed over the iterations
     long long total_repairs;
     unsigned long long t_mark;      // globaltimer at the end of the previous solve/update
     unsigned long long t_corr_ns;   // accumulated correspondence-search time (both phases)

@@ -66,6 +66,7 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->work_count = 0;
         st->corr_stamped = 0;
         st->total_repairs = 0;
+        st->searched_total = 0;
         st->t_corr_ns = 0;
         st->t_corr_se3_ns = 0;
         st->t_start = global_timer_ns();
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterSt
     if (st->iter >= 1000000) st->done = 1;  // hard cap (the reference would spin forever on such parameters)
     st->total_repairs += st->repair_count;
     st->repair_count = 0;
+    st->searched_total += (unsigned long long)st->work_count;
     st->work_count = 0;
     st->corr_stamped = 0;
     st->t_mark = global_timer_ns();
