@@ -35,7 +35,7 @@ import workloads as W  # noqa: E402
 METRIC = "SE(3)-ICP registrations/s @KITTI-size clouds (se3_gicp)"
 UNIT = "registrations/s"
 UNIQUE_PAIRS = 8  # distinct synthetic scenes per GPU, cycled to pairs_per_gpu
-NCU_TRAFFIC_BYTES = 32661504  # see roofline.traffic below
+NCU_TRAFFIC_BYTES = 33188096  # see roofline.traffic below (31 603 456 read + 1 584 640 written)
 
 
 def parse():
@@ -322,7 +322,7 @@ def run_b200(args):
         achieved = alg_bytes / (ms_nn * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum of nn_search_kernel, first launch of a pair (full 12-D
-                    # search of every query), ncu --set full capture summarised in profiles/r1_summary_v4.md
+                    # search of every query), ncu --set full capture summarised in profiles/r1_summary_v5.md
                     "traffic": NCU_TRAFFIC_BYTES,
                     "kernel": "SE(3) correspondence stage: nn_filter_kernel + nn_search_kernel",
                     "algorithmic_bytes": alg_bytes, "kernel_ms": ms_nn, "launches_averaged": se3_launches,
