@@ -44,79 +44,74 @@ public:
     IterativeSE3Registration(const IterativeSE3Registration&) = delete;
     IterativeSE3Registration& operator=(const IterativeSE3Registration&) = delete;
 
-    // ---- input (reference hpp:31-34, .cpp:350-376): file overloads replace, cloud overloads append
-    void setSourceCloud(const std::string& filename);
-    void setTargetCloud(const std::string& filename);
-    void setSourceCloud(const open3d::geometry::PointCloud& cloud);
-    void setTargetCloud(const open3d::geometry::PointCloud& cloud);
+    // ================= configuration: plain public fields, assigned by the drivers before run_*() =================
+    // (reference hpp:80-95; constructor defaults .cpp:334-348, repeated in se3icp_default_params)
+    int max_num_iterations_;      // 150   total iteration budget
+    int max_num_se3_iterations_;  // 20    budget of the SE(3) phase
+    int number_of_nn_for_LRF_;    // 30    neighbours of the TOLDI frame
+    double mse_;                  // 1e-5  stop threshold on the change of the mean correspondence distance
+    double mse_switch_error_;     // 1e-3  phase switch on ||T_prev - T||_F
+    double estimated_overlap_;    // 1.0   overlap ratio of the trimmed rejector
+    double alpha_rot;             // 3.0   rotation weight of the SE(3) metric
+    double beta_transl;           // 1.0   translation weight
+    double scale_preprocessing;   // 3.0   clouds are scaled to this radius
+    double lrf_radius_;           // 0.8   SHOT frame radius (unused by every entry point, kept for compatibility)
 
-    // ---- single correspondence passes (reference hpp:36-38, .cpp:402-470); the tree arguments are
-    //      accepted for signature compatibility, the search structures live on the GPU
-    void update_correspondences_kd_tree_XYZ(const open3d::geometry::KDTreeFlann& target_kd_tree);
-    void update_correspondences_raw_flann_SE3();
-    void update_correspondences_raw_flann_SE3(const open3d::geometry::KDTreeFlann& se3_tree,
-                                              const std::vector<Eigen::Matrix4d>& cloud_vector);
+    // ================= results of a run_*() call ====================================================================
+    Eigen::Matrix4d current_estimated_T_;          // source -> target, original coordinates
+    int num_iterations_;                           // iterations executed
+    int num_pure_se3_iterations_;                  // ... of which in the SE(3) phase (-1 for run_icp)
+    double time_se3_correspondence_search_;        // ms, run_se3_icp_with_cf (hpp:86)
+    double time_before_pure_icp_;                  // ms, run_se3_icp_with_cf (hpp:85)
+    std::vector<Eigen::Matrix4d> estimated_history_;  // per-iteration increments (run_icp, hpp:63)
 
-    // ---- mean correspondence distance (reference hpp:40-43, .cpp:379-400)
-    double estimate_current_mse(const pcl::Correspondences pcl_corrs);
-    double estimate_current_mse_compute_euclidean(const open3d::geometry::PointCloud& cloud_src,
-                                                  const open3d::geometry::PointCloud& cloud_tgt,
-                                                  const pcl::Correspondences pcl_corrs);
-
-    // ---- registration entry points (reference hpp:46-50); variant_name: "pt2pt" | "pt2pl" | "gicp"
-    void run_icp(const std::string& variant_name);       // reference .cpp:473-552
-    void run_se3_icp(const std::string& variant_name);   // reference .cpp:555-739
-    void run_se3_icp_with_cf();                          // reference .cpp:742-959
-    void run_se3_pure(const std::string& variant_name);  // reference .cpp:962-1128
-
-    // ---- extensions (not in the reference) ------------------------------------------------------------
-    // Copies the device-side state the reference keeps in public members (SE(3) clouds, correspondence
-    // sets) back to the host after a run.  Off by default: no reference driver reads them.
-    void set_mirror_state(bool on) { mirror_state_ = on; }
-    // 0 = keep the smallest distances in the trimmed rejector (documented PCL intent), 1 = keep the largest
-    void set_trim_keep_largest(bool on) { trim_keep_largest_ = on; }
-    // CUDA device ordinal used by this object (default: environment SE3ICP_DEVICE or 0)
-    void set_device(int device);
-
-    // ---- public state, as in the reference (hpp:53-98) ------------------------------------------------
+    // ================= clouds =========================================================================================
+    // file overloads replace the cloud, cloud overloads append to it (reference hpp:31-34, .cpp:350-376)
+    void setSourceCloud(const std::string& ply_file);
+    void setTargetCloud(const std::string& ply_file);
+    void setSourceCloud(const open3d::geometry::PointCloud& points);
+    void setTargetCloud(const open3d::geometry::PointCloud& points);
     open3d::geometry::PointCloud source_;
     open3d::geometry::PointCloud source_moving_;
     open3d::geometry::PointCloud target_;
 
+    // ================= registration entry points (reference hpp:46-50) ================================================
+    // variant: "pt2pt" | "pt2pl" | "gicp"; anything else prints the reference's message
+    void run_se3_icp(const std::string& variant);   // SE(3) phase, then plain ICP   (.cpp:555-739)
+    void run_se3_icp_with_cf();                     // GICP with depth confidences   (.cpp:742-959)
+    void run_se3_pure(const std::string& variant);  // SE(3) phase only              (.cpp:962-1128)
+    void run_icp(const std::string& variant);       // plain ICP                     (.cpp:473-552)
+
+    // ================= single passes and helpers (reference hpp:36-43) ================================================
+    // One correspondence pass on the current state (.cpp:402-470).  The kd-tree arguments exist for signature
+    // compatibility only: the search structures live on the GPU.
+    void update_correspondences_raw_flann_SE3();
+    void update_correspondences_raw_flann_SE3(const open3d::geometry::KDTreeFlann& unused_tree,
+                                              const std::vector<Eigen::Matrix4d>& se3_cloud);
+    void update_correspondences_kd_tree_XYZ(const open3d::geometry::KDTreeFlann& unused_tree);
+    // mean of the stored correspondence distances / of recomputed Euclidean distances (.cpp:379-400)
+    double estimate_current_mse(const pcl::Correspondences correspondences);
+    double estimate_current_mse_compute_euclidean(const open3d::geometry::PointCloud& src, const open3d::geometry::PointCloud& tgt,
+                                                  const pcl::Correspondences correspondences);
+
+    // ================= state the reference keeps in public members ====================================================
+    // Filled after a run only when set_mirror_state(true): no reference driver reads them (hpp:59-60,74-75).
     std::vector<Eigen::Matrix4d> source_se3_cloud_;
     std::vector<Eigen::Matrix4d> target_se3_cloud_;
-
-    std::vector<Eigen::Matrix4d> estimated_history_;
-
-    open3d::geometry::KDTreeFlann kd_tree_target_XYZ;
-    open3d::geometry::KDTreeFlann kd_tree_source_XYZ;
-    open3d::geometry::KDTreeFlann raw_flann_kd_tree_target_SE3;
-
     CorrespondencesSet current_correspondences_set;
     pcl::CorrespondencesPtr current_correspondences_set_pcl;
+    // Present so that code naming them still compiles; the GPU path does not use them (hpp:66-68,76-78).
+    open3d::geometry::KDTreeFlann kd_tree_source_XYZ;
+    open3d::geometry::KDTreeFlann kd_tree_target_XYZ;
+    open3d::geometry::KDTreeFlann raw_flann_kd_tree_target_SE3;
     open3d::pipelines::registration::TransformationEstimationPointToPoint o3d_estimator;
     open3d::pipelines::registration::TransformationEstimationPointToPlane o3d_estimator_po2pl;
     open3d::pipelines::registration::TransformationEstimationForGeneralizedICP o3d_estimator_generalized;
 
-    int number_of_nn_for_LRF_;
-    double mse_;
-    double estimated_overlap_;
-    double lrf_radius_;
-    double mse_switch_error_;
-    double time_before_pure_icp_;
-    double time_se3_correspondence_search_;
-
-    double alpha_rot;
-    double beta_transl;
-    double scale_preprocessing;
-
-    int num_iterations_;
-    int max_num_iterations_;
-    int max_num_se3_iterations_;
-    int num_pure_se3_iterations_;
-
-    // result of a run_*() call
-    Eigen::Matrix4d current_estimated_T_;
+    // ================= extensions (not in the reference) ==============================================================
+    void set_mirror_state(bool on) { mirror_state_ = on; }            // copy SE(3) clouds / correspondences back after a run
+    void set_trim_keep_largest(bool on) { trim_keep_largest_ = on; }  // other reading of PCL's comparator
+    void set_device(int device);                                      // CUDA ordinal (default: SE3ICP_DEVICE or 0)
 
 private:
     se3icp_ctx* context();

@@ -93,22 +93,22 @@ double largestDistanceFromGivenPoint(const Eigen::Vector3d& ref_point, const ope
     return largest;
 }
 
-IterativeSE3Registration::IterativeSE3Registration()
-    : current_correspondences_set_pcl(new pcl::Correspondences),
+IterativeSE3Registration::IterativeSE3Registration()  // defaults of the reference constructor, .cpp:334-348
+    : max_num_iterations_(150),
+      max_num_se3_iterations_(20),
       number_of_nn_for_LRF_(30),
       mse_(0.00001),
-      estimated_overlap_(1.0),
-      lrf_radius_(0.8),
       mse_switch_error_(0.001),
-      time_before_pure_icp_(0.0),
-      time_se3_correspondence_search_(0.0),
+      estimated_overlap_(1.0),
       alpha_rot(3.0),
       beta_transl(1.0),
       scale_preprocessing(3.0),
+      lrf_radius_(0.8),
       num_iterations_(0),
-      max_num_iterations_(150),
-      max_num_se3_iterations_(20),
-      num_pure_se3_iterations_(-1) {
+      num_pure_se3_iterations_(-1),
+      time_se3_correspondence_search_(0.0),
+      time_before_pure_icp_(0.0),
+      current_correspondences_set_pcl(new pcl::Correspondences) {
     current_estimated_T_.setIdentity();
     const char* dev = std::getenv("SE3ICP_DEVICE");
     device_ = dev ? std::atoi(dev) : 0;
