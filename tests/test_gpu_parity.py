@@ -551,3 +551,37 @@ def test_swap_clouds_registers_the_inverse_problem(ctx, capi, c1):
     ctx.set_cloud(capi.TARGET, src)
     T_ref, _ = ctx.run(p)
     np.testing.assert_allclose(T_bwd, T_ref, rtol=0, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Ragged and tiny inputs: fewer points than the neighbourhood sizes, unequal cloud sizes, partial last leaves.
+@pytest.mark.parametrize("n_src,n_tgt", [(40, 40), (33, 500), (500, 33), (95, 1000), (1025, 257)])
+@pytest.mark.parametrize("variant", ["pt2pt", "pt2pl", "gicp"])
+def test_registration_ragged_sizes(ctx, orc, capi, variant, n_src, n_tgt):
+    rng = np.random.default_rng(n_src * 7919 + n_tgt)
+    base = W.load_bunny()
+    T = W.make_T(W.rot_3d(0.05, -0.04, 0.08), [0.4, -0.3, 0.2])
+    tgt = base[rng.choice(len(base), n_tgt, replace=False)]
+    src = W.apply_T(np.linalg.inv(T), base[rng.choice(len(base), n_src, replace=False)])
+    kw = dict(RRM, max_num_iterations=30)
+    Tg, sg, To, so = run_both(ctx, orc, capi, src, tgt, "RUN_SE3_ICP", variant, **kw)
+    assert (sg.num_iterations, sg.num_pure_se3_iterations) == (so.num_iterations, so.num_pure_se3_iterations)
+    if np.all(np.isfinite(To)):
+        assert_transform_parity(Tg, To, tgt)
+    else:  # a degenerate system may produce NaN in the reference arithmetic; the CUDA path must do the same
+        assert np.array_equal(np.isfinite(Tg), np.isfinite(To))
+
+
+def test_empty_cloud_is_an_error_not_a_crash(pkg, capi, c1):
+    src, tgt, _ = c1
+    ctx = capi.Context(0)
+    ctx.set_cloud(capi.SOURCE, src)
+    with pytest.raises(RuntimeError):
+        ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM))  # no target
+    ctx.set_cloud(capi.TARGET, np.zeros((0, 3)))
+    with pytest.raises(RuntimeError):
+        ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM))
+    ctx.set_cloud(capi.TARGET, tgt)
+    T, st = ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM))  # and the context still works
+    assert st.num_iterations == 8
+    ctx.close()
