@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=32)
-    ap.add_argument("--contexts", type=int, default=8, help="concurrent registration contexts (streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=16, help="concurrent registration contexts (streams) per GPU")
     ap.add_argument("--n-az", type=int, default=1900, help="azimuth steps of the synthetic 64-ring scanner")
     return ap.parse_args()
 
