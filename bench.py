@@ -11,10 +11,12 @@ independent pairs (32 -> 256 pairs at 8 GPUs, the named configuration); no data-
             (se3icp_run_batch_device), CUDA-event timed, max over ranks
   e2e       same through the host-buffer C-ABI call a reference user makes (se3icp_run_batch from
             pinned host memory: H2D of both scans + D2H of the 4x4 result inside the timed region)
-  roofline  the dominant kernel (SE(3) 12-D nearest-neighbour sweep) against the measured HBM peak:
-            algorithmic bytes 48 N + 48 M + 8 N per launch / live CUDA-event time
-  cpu_baseline  the CPU oracle (a port: the reference needs Open3D/PCL/Eigen, absent here) timed on
-            the host cores on one pair of the same workload
+  roofline  the dominant stage (SE(3) 12-D correspondence search: nn_filter_kernel + nn_search_kernel) against the
+            measured HBM peak: algorithmic bytes 48 N + 48 M + 8 N per launch / live device-side time
+            of the stage, averaged over the SE(3) iterations of the unique pairs
+  cpu_baseline  the CPU oracle (a port) timed on the host cores over the 8 unique pairs of the same workload, N = 1
+            only; the reference's own source, compiled against stand-in Open3D/PCL/Eigen (oracle/_ref), is 3-4x slower
+            than the port and is reported next to it, not as the baseline
   --impl reference   times only that CPU path (rank 0), same metric/config
 """
 import argparse
