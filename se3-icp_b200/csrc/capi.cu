@@ -96,7 +96,7 @@ TargetView se3icp_ctx::target_view() const {
     T.conf = conf[1].as<double>();
     T.rows32 = se3idx.rows32.as<float4>();
     T.rows64 = se3idx.rows64.as<double>();
-    T.box12 = se3idx.box12.as<float>();
+    T.box12 = se3idx.box12.as<float2>();
     T.perm12 = se3idx.perm12.as<int>();
     T.inv12 = se3idx.inv12.as<int>();
     T.keys12 = se3idx.keys12.as<uint64_t>();

@@ -120,7 +120,7 @@ struct TargetView {
     // SE(3) search structure: rows in 6-D Morton order (se3_index.cu); level layout shared with idx
     const float4* rows32; // [3][n]  (alpha R | tscale p) as floats
     const double* rows64; // [12][n]
-    const float* box12;   // [24][total_nodes] lo[12], hi[12]
+    const float2* box12;  // [12][total_nodes] (lo, hi) per dimension, rounded outwards
     const int* perm12;    // 6-D position -> original index
     const int* inv12;     // original index -> 6-D position
     const uint64_t* keys12;

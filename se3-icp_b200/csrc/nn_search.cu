@@ -369,12 +369,12 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     const float qeps = qamax * 1.1920929e-07f;  // 2^-23 |q|max: twice the worst rounding of any coordinate
     // rigorous FP32 lower bound: every operation rounds toward the smaller result
     auto lb_fn = [&](int node) -> double {
-        const float* b = T.box12 + node;
+        const float2* b = T.box12 + node;
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < 12; k++) {
-            float lo = b[(size_t)k * tn], hi = b[(size_t)(12 + k) * tn];
-            float d = fmaxf(__fsub_rd(lo, qf[k]), __fsub_rd(qf[k], hi));
+            const float2 lh = b[(size_t)k * tn];
+            float d = fmaxf(__fsub_rd(lh.x, qf[k]), __fsub_rd(qf[k], lh.y));
             d = fmaxf(0.f, __fsub_rd(d, qeps));
             acc = __fadd_rd(acc, __fmul_rd(d, d));
         }

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) pack_se3_rows_kernel(const double* __rest
 }
 
 __global__ void __launch_bounds__(256) box12_leaf_kernel(const double* __restrict__ rows64, int n, int n_leaves,
-                                                          int total_nodes, float* __restrict__ box12) {
+                                                          int total_nodes, float2* __restrict__ box12) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_leaves) return;
     int p = warp * 32 + lane;
@@ -72,15 +72,12 @@ __global__ void __launch_bounds__(256) box12_leaf_kernel(const double* __restric
         if (p < n) lo = hi = rows64[k * nn + p];
         lo = warp_min(lo);
         hi = warp_max(hi);
-        if (lane == 0) {
-            box12[(size_t)k * tn + warp] = __double2float_rd(lo);
-            box12[(size_t)(12 + k) * tn + warp] = __double2float_ru(hi);
-        }
+        if (lane == 0) box12[(size_t)k * tn + warp] = make_float2(__double2float_rd(lo), __double2float_ru(hi));
     }
 }
 
 __global__ void __launch_bounds__(256) box12_upper_kernel(int child_off, int child_cnt, int node_off, int node_cnt,
-                                                           int total_nodes, float* __restrict__ box12) {
+                                                           int total_nodes, float2* __restrict__ box12) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= node_cnt) return;
     int c = warp * 32 + lane;
@@ -89,15 +86,13 @@ __global__ void __launch_bounds__(256) box12_upper_kernel(int child_off, int chi
     for (int k = 0; k < 12; k++) {
         float lo = 3.0e38f, hi = -3.0e38f;
         if (c < child_cnt) {
-            lo = box12[(size_t)k * tn + child_off + c];
-            hi = box12[(size_t)(12 + k) * tn + child_off + c];
+            const float2 lh = box12[(size_t)k * tn + child_off + c];
+            lo = lh.x;
+            hi = lh.y;
         }
         lo = warp_minf(lo);
         hi = warp_maxf(hi);
-        if (lane == 0) {
-            box12[(size_t)k * tn + node_off + warp] = lo;
-            box12[(size_t)(12 + k) * tn + node_off + warp] = hi;
-        }
+        if (lane == 0) box12[(size_t)k * tn + node_off + warp] = make_float2(lo, hi);
     }
 }
 
@@ -134,10 +129,10 @@ int Se3IndexStorage::build(const CloudIndex& I, const double* frame, double alph
                                              rows64.as<double>(), inv12.as<int>(), state);
     int n_leaves = I.level_cnt[0];
     box12_leaf_kernel<<<(n_leaves * 32 + 255) / 256, 256, 0, st>>>(rows64.as<double>(), n, n_leaves, I.total_nodes,
-                                                                   box12.as<float>());
+                                                                   box12.as<float2>());
     for (int l = 1; l < I.n_levels; l++)
         box12_upper_kernel<<<(I.level_cnt[l] * 32 + 255) / 256, 256, 0, st>>>(
-            I.level_off[l - 1], I.level_cnt[l - 1], I.level_off[l], I.level_cnt[l], I.total_nodes, box12.as<float>());
+            I.level_off[l - 1], I.level_cnt[l - 1], I.level_off[l], I.level_cnt[l], I.total_nodes, box12.as<float2>());
     SE3_CUDA(cudaGetLastError());
     if (launches) *launches += 3 + I.n_levels + 3;
     return 0;
