@@ -40,7 +40,7 @@ struct CloudIndex {
     const int* perm = nullptr;      // Morton position -> original index
     const int* inv = nullptr;       // original index -> Morton position
     const uint64_t* keys = nullptr;
-    const float* box = nullptr;     // [6][total_nodes]
+    const float2* box = nullptr;    // [3][total_nodes] (lo, hi) per axis, rounded outwards
     const double* bbox = nullptr;   // device: lo[3], hi[3] of the cloud (for Morton quantisation)
 };
 

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const double* __rest
 // leaves: one warp per 32 consecutive Morton points; boxes rounded outward to float
 __global__ void __launch_bounds__(256) leaf_box_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
                                                         const double* __restrict__ sz, int n, int n_leaves, int total_nodes,
-                                                        float* __restrict__ box) {
+                                                        float2* __restrict__ box) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_leaves) return;
     int p = warp * 32 + lane;
@@ -261,16 +261,13 @@ __global__ void __launch_bounds__(256) leaf_box_kernel(const double* __restrict_
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         double a = warp_min(lo[d]), b = warp_max(hi[d]);
-        if (lane == 0) {
-            box[(size_t)d * total_nodes + warp] = __double2float_rd(a);
-            box[(size_t)(3 + d) * total_nodes + warp] = __double2float_ru(b);
-        }
+        if (lane == 0) box[(size_t)d * total_nodes + warp] = make_float2(__double2float_rd(a), __double2float_ru(b));
     }
 }
 
 // upper levels: one warp per node, union of up to 32 child boxes
 __global__ void __launch_bounds__(256) upper_box_kernel(int child_off, int child_cnt, int node_off, int node_cnt,
-                                                         int total_nodes, float* __restrict__ box) {
+                                                         int total_nodes, float2* __restrict__ box) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= node_cnt) return;
     int c = warp * 32 + lane;
@@ -278,17 +275,15 @@ __global__ void __launch_bounds__(256) upper_box_kernel(int child_off, int child
     if (c < child_cnt) {
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            lo[d] = box[(size_t)d * total_nodes + child_off + c];
-            hi[d] = box[(size_t)(3 + d) * total_nodes + child_off + c];
+            const float2 lh = box[(size_t)d * total_nodes + child_off + c];
+            lo[d] = lh.x;
+            hi[d] = lh.y;
         }
     }
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         float a = warp_minf(lo[d]), b = warp_maxf(hi[d]);
-        if (lane == 0) {
-            box[(size_t)d * total_nodes + node_off + warp] = a;
-            box[(size_t)(3 + d) * total_nodes + node_off + warp] = b;
-        }
+        if (lane == 0) box[(size_t)d * total_nodes + node_off + warp] = make_float2(a, b);
     }
 }
 
@@ -349,7 +344,7 @@ int IndexStorage::reserve(int n) {
     view.sz = sz.as<double>();
     view.perm = perm.as<int>();
     view.keys = keys.as<uint64_t>();
-    view.box = box.as<float>();
+    view.box = box.as<float2>();
     view.bbox = bbox.as<double>();
     return 0;
 }
@@ -372,11 +367,11 @@ int IndexStorage::build(cudaStream_t st, long long* launches) {
                                              sx.as<double>(), sy.as<double>(), sz.as<double>(), vals_tmp.as<int>());
     int n_leaves = view.level_cnt[0];
     leaf_box_kernel<<<(n_leaves * 32 + 255) / 256, 256, 0, st>>>(sx.as<double>(), sy.as<double>(), sz.as<double>(), n,
-                                                                 n_leaves, view.total_nodes, box.as<float>());
+                                                                 n_leaves, view.total_nodes, box.as<float2>());
     for (int l = 1; l < view.n_levels; l++) {
         upper_box_kernel<<<(view.level_cnt[l] * 32 + 255) / 256, 256, 0, st>>>(
             view.level_off[l - 1], view.level_cnt[l - 1], view.level_off[l], view.level_cnt[l], view.total_nodes,
-            box.as<float>());
+            box.as<float2>());
     }
     SE3_CUDA(cudaGetLastError());
     if (launches) *launches += 6 + (view.n_levels - 1) + 3;  // + CUB's internal passes (approx.)

@@ -12,10 +12,11 @@ namespace se3 {
 constexpr int kStackEntries = 192;  // >= 31 * levels + 1 for up to 6 levels (n <= 32^6)
 
 __device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node, double qx, double qy, double qz) {
-    const float* b = I.box + node;
+    const float2* b = I.box + node;
     size_t tn = (size_t)I.total_nodes;
-    double lox = b[0], loy = b[tn], loz = b[2 * tn];
-    double hix = b[3 * tn], hiy = b[4 * tn], hiz = b[5 * tn];
+    const float2 bx = b[0], by = b[tn], bz = b[2 * tn];
+    double lox = bx.x, loy = by.x, loz = bz.x;
+    double hix = bx.y, hiy = by.y, hiz = bz.y;
     double dx = fmax(0.0, fmax(lox - qx, qx - hix));
     double dy = fmax(0.0, fmax(loy - qy, qy - hiy));
     double dz = fmax(0.0, fmax(loz - qz, qz - hiz));
