@@ -376,7 +376,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
             const float2 lh = b[(size_t)k * tn];
             float d = fmaxf(__fsub_rd(lh.x, qf[k]), __fsub_rd(qf[k], lh.y));
             d = fmaxf(0.f, __fsub_rd(d, qeps));
-            acc = __fadd_rd(acc, __fmul_rd(d, d));
+            acc = __fmaf_rd(d, d, acc);  // exact d*d + acc rounded down: still a lower bound, one instruction
         }
         return (double)acc;
     };
