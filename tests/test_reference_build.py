@@ -105,3 +105,30 @@ def test_se3_correspondences_match_reference_source():
     idx_o, d2_o = orc.nn(rows_s, rows_t)
     assert np.array_equal(idx_o, idx_r)
     np.testing.assert_allclose(np.linalg.norm(cs - ct[idx_r], axis=1), dist_r, rtol=0, atol=1e-12)
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(16))
+def test_oracle_matches_reference_source_on_random_problems(seed):
+    """Randomised sweep over entries, variants and every public parameter on small ragged clouds: the oracle and the
+    reference's own source must agree on the iteration counters and, to rounding, on the transform."""
+    rng = np.random.default_rng(1234 + seed)
+    base = W.load_bunny()
+    n_s, n_t = int(rng.integers(300, 1500)), int(rng.integers(300, 1500))
+    T = W.make_T(W.rot_3d(*rng.uniform(-0.3, 0.3, 3)), rng.uniform(-1.0, 1.0, 3))
+    tgt = base[rng.choice(len(base), n_t, replace=False)] + rng.normal(0, 0.02, (n_t, 3))
+    src = W.apply_T(np.linalg.inv(T), base[rng.choice(len(base), n_s, replace=False)] + rng.normal(0, 0.02, (n_s, 3)))
+    entry = ["icp", "se3", "se3", "pure", "cf"][seed % 5]
+    variant = "gicp" if entry == "cf" else ["pt2pt", "pt2pl", "gicp"][(seed // 5 + seed) % 3]
+    params = dict(max_num_iterations=int(rng.integers(5, 40)), max_num_se3_iterations=int(rng.integers(2, 12)),
+                  number_of_nn_for_LRF=int(rng.choice([12, 30, 45, 90])), mse=float(10 ** rng.uniform(-7, -4)),
+                  mse_switch_error=float(10 ** rng.uniform(-5, -2)), estimated_overlap=float(rng.choice([1.0, 0.9, 0.73, 0.5])),
+                  alpha_rot=float(rng.uniform(0.5, 4.0)), beta_transl=float(rng.uniform(0.5, 2.0)),
+                  scale_preprocessing=float(rng.uniform(1.0, 5.0)), trim_keep_largest=int(seed % 7 == 3))
+    Tr, it, it_se3 = RB.run(MG.ENTRY_OF[entry], variant, src, tgt, RB.default_params(**params))
+    To, st, _ = orc.run(src, tgt, orc.default_params(variant=variant, entry=ENTRY_ID[entry], **params))
+    assert (st.num_iterations, st.num_pure_se3_iterations) == (it, it_se3), (entry, variant, params)
+    if np.all(np.isfinite(Tr)):
+        assert np.abs(To - Tr).max() < 1e-8 * max(1.0, float(np.abs(tgt).max())), (entry, variant, params)
+    else:
+        assert np.array_equal(np.isfinite(To), np.isfinite(Tr))
