@@ -585,3 +585,36 @@ def test_empty_cloud_is_an_error_not_a_crash(pkg, capi, c1):
     T, st = ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM))  # and the context still works
     assert st.num_iterations == 8
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# CUDA path against the reference's own source, live: oracle/_ref/libse3icp_reference.so is built where /root/reference
+# exists and travels to the GPU box with the snapshot (it is not read from /root/reference at run time).
+from oracle import reference_build as _RB  # noqa: E402
+
+
+@pytest.mark.skipif(not os.path.exists(_RB.LIB_PATH), reason="oracle/_ref/libse3icp_reference.so did not travel")
+@pytest.mark.parametrize("seed", range(10))
+def test_cuda_path_matches_reference_source_on_random_problems(ctx, capi, seed):
+    rng = np.random.default_rng(4321 + seed)
+    base = W.load_bunny()
+    n_s, n_t = int(rng.integers(300, 1500)), int(rng.integers(300, 1500))
+    T = W.make_T(W.rot_3d(*rng.uniform(-0.3, 0.3, 3)), rng.uniform(-1.0, 1.0, 3))
+    tgt = base[rng.choice(len(base), n_t, replace=False)] + rng.normal(0, 0.02, (n_t, 3))
+    src = W.apply_T(np.linalg.inv(T), base[rng.choice(len(base), n_s, replace=False)] + rng.normal(0, 0.02, (n_s, 3)))
+    entry = ["icp", "se3", "se3", "pure", "cf"][seed % 5]
+    variant = "gicp" if entry == "cf" else ["pt2pt", "pt2pl", "gicp"][(seed // 5 + seed) % 3]
+    params = dict(max_num_iterations=int(rng.integers(5, 40)), max_num_se3_iterations=int(rng.integers(2, 12)),
+                  number_of_nn_for_LRF=int(rng.choice([12, 30, 45, 90])), mse=float(10 ** rng.uniform(-7, -4)),
+                  mse_switch_error=float(10 ** rng.uniform(-5, -2)), estimated_overlap=float(rng.choice([1.0, 0.9, 0.73, 0.5])),
+                  alpha_rot=float(rng.uniform(0.5, 4.0)), beta_transl=float(rng.uniform(0.5, 2.0)),
+                  scale_preprocessing=float(rng.uniform(1.0, 5.0)), trim_keep_largest=int(seed % 7 == 3))
+    Tr, it, it_se3 = _RB.run(_MG.ENTRY_OF[entry], variant, src, tgt, _RB.default_params(**params))
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    Tg, sg = ctx.run(capi.default_params(variant=variant, entry=getattr(capi, REF_ENTRY[entry]), **params))
+    assert (sg.num_iterations, sg.num_pure_se3_iterations) == (it, it_se3), (entry, variant, params)
+    if np.all(np.isfinite(Tr)):
+        assert_transform_parity(Tg, Tr, tgt)
+    else:
+        assert np.array_equal(np.isfinite(Tg), np.isfinite(Tr))
