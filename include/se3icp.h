@@ -83,7 +83,9 @@ typedef struct se3icp_params {
     int32_t record_history;         /* 1 = keep per-iteration T_i (reference estimated_history_, hpp:63) */
     int32_t nn_coherence;           /* 1 = SE(3) search may skip queries whose previous match is provably still nearest */
     int32_t reuse_features;         /* 1 = keep a cloud's LRFs / normals / covariances across runs while the cloud stays in the
-                                       context (se3icp_swap_clouds, se3icp_run_sequence); 0 = recompute every run */
+                                       context (se3icp_swap_clouds, se3icp_run_sequence); 0 = recompute every run.
+                                       se3icp_set_cloud / se3icp_set_cloud_device always invalidate them, so a caller who
+                                       rewrites a caller-owned device buffer in place must set the cloud again */
 } se3icp_params;
 
 typedef struct se3icp_stats {
