@@ -41,8 +41,9 @@ class IterativeSE3Registration {
 public:
     IterativeSE3Registration();
     ~IterativeSE3Registration();
-    IterativeSE3Registration(const IterativeSE3Registration&) = delete;
-    IterativeSE3Registration& operator=(const IterativeSE3Registration&) = delete;
+    // copyable like the reference class: a copy takes the fields and clouds and gets a GPU context of its own on first use
+    IterativeSE3Registration(const IterativeSE3Registration& other);
+    IterativeSE3Registration& operator=(const IterativeSE3Registration& other);
 
     // ================= configuration: plain public fields, assigned by the drivers before run_*() =================
     // (reference hpp:80-95; constructor defaults .cpp:334-348, repeated in se3icp_default_params)
@@ -95,7 +96,9 @@ public:
                                                   const pcl::Correspondences correspondences);
 
     // ================= state the reference keeps in public members ====================================================
-    // Filled after a run only when set_mirror_state(true): no reference driver reads them (hpp:59-60,74-75).
+    // Filled after a run only when set_mirror_state(true): no reference driver reads them (hpp:59-60,74-75).  With the
+    // mirror on, run_*() also leaves source_ / target_ centred and scaled and source_moving_ at the estimate, as the
+    // reference does (.cpp:568-582,706), so a second run_*() on the same object starts from the same state as upstream.
     std::vector<Eigen::Matrix4d> source_se3_cloud_;
     std::vector<Eigen::Matrix4d> target_se3_cloud_;
     CorrespondencesSet current_correspondences_set;
@@ -109,8 +112,9 @@ public:
     open3d::pipelines::registration::TransformationEstimationForGeneralizedICP o3d_estimator_generalized;
 
     // ================= extensions (not in the reference) ==============================================================
-    void set_mirror_state(bool on) { mirror_state_ = on; }            // copy SE(3) clouds / correspondences back after a run
-    void set_trim_keep_largest(bool on) { trim_keep_largest_ = on; }  // other reading of PCL's comparator
+    void set_mirror_state(bool on) { mirror_state_ = on; }            // reproduce the reference's post-run member state
+    void set_trim_keep_largest(bool on) { trim_keep_largest_ = on; }  // false: keep the smallest distances instead of PCL's
+                                                                      // `distance >` comparator (include/se3icp.h)
     void set_device(int device);                                      // CUDA ordinal (default: SE3ICP_DEVICE or 0)
 
 private:
@@ -121,5 +125,5 @@ private:
     se3icp_ctx* ctx_ = nullptr;
     int device_ = -1;
     bool mirror_state_ = false;
-    bool trim_keep_largest_ = false;
+    bool trim_keep_largest_ = true;
 };

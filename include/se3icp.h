@@ -54,8 +54,7 @@ enum se3icp_nn_mode {
     SE3ICP_NN_AUTO = 0,       /* library picks per iteration */
     SE3ICP_NN_BRUTE_F32 = 1,  /* tiled FP32 brute force + certification + exact FP64 repair */
     SE3ICP_NN_EXACT_F64 = 2,  /* FP64 brute force for every query (slow; test oracle on device) */
-    SE3ICP_NN_TREE = 3,       /* pruned traversal of the 12-D bounded hierarchy, FP64 leaves */
-    SE3ICP_NN_TENSOR = 4      /* tcgen05 TF32 contraction sweep + exact repair */
+    SE3ICP_NN_TREE = 3        /* pruned traversal of the 12-D bounded hierarchy, FP64 leaves */
 };
 
 enum se3icp_which { SE3ICP_SOURCE = 0, SE3ICP_TARGET = 1 };
@@ -70,7 +69,11 @@ typedef struct se3icp_params {
     int32_t number_of_nn_for_LRF;   /* 30 */
     int32_t knn_normals_pt2pl;      /* 30 (Open3D EstimateNormals default, .cpp:494,643) */
     int32_t knn_normals_gicp;       /* 20 (.cpp:43) */
-    int32_t trim_keep_largest;      /* 0 = keep the smallest distances */
+    int32_t trim_keep_largest;      /* 1 (default) = what PCL 1.14 does: CorrespondenceRejectorTrimmed runs std::nth_element
+                                       with pcl::isBetterCorrespondence, which is `pc1.distance > pc2.distance`, so the
+                                       floor(overlap * N) correspondences with the LARGEST distances survive.  0 = keep the
+                                       smallest (what the class documentation says it does).  PCL is not installed here, so
+                                       the comparator is restated from its published source, not verified */
     double mse;                     /* 1e-5 */
     double mse_switch_error;        /* 1e-3 */
     double estimated_overlap;       /* 1.0 */
@@ -124,7 +127,11 @@ int se3icp_set_cloud_device(se3icp_ctx* ctx, int which, const double* d_xyz_aos,
 
 /* replaces run_icp / run_se3_icp / run_se3_icp_with_cf / run_se3_pure.  T_out row-major 4x4. */
 int se3icp_run(se3icp_ctx* ctx, const se3icp_params* p, double* T_out, se3icp_stats* stats);
-/* asynchronous form: enqueue everything on the context's stream, read back later */
+/* asynchronous form: enqueue everything on the context's stream, read back later.  Truly asynchronous only with
+ * params.use_graph (the default): the host-driven loop (use_graph = 0, or a process running under Nsight Compute)
+ * synchronises once per iteration inside se3icp_run_async.  While a run is pending every entry point that would
+ * reallocate or overwrite its buffers (set_cloud*, swap_clouds, run_async, run_sharded, the stage-level calls)
+ * returns SE3ICP_ERR_STATE until se3icp_run_finish has been called. */
 int se3icp_run_async(se3icp_ctx* ctx, const se3icp_params* p);
 int se3icp_run_finish(se3icp_ctx* ctx, double* T_out, se3icp_stats* stats);
 
@@ -179,7 +186,9 @@ int se3icp_run_sharded(se3icp_ctx* ctx, const se3icp_params* p, size_t src_begin
 enum se3icp_stage { SE3ICP_STAGE_NN_SE3 = 0, SE3ICP_STAGE_NN_XYZ = 1, SE3ICP_STAGE_REDUCE = 2, SE3ICP_STAGE_KNN_TARGET = 3 };
 int se3icp_time_stage(se3icp_ctx* ctx, int stage, int repeats, double* ms_avg);
 
-/* ---------------- stage-level entry points (parity tests; one per row of SURVEY §8a) ---------------- */
+/* ---------------- stage-level entry points (parity tests; one per row of SURVEY §8a) ----------------
+ * They borrow the context's cloud slots and work buffers: after any of them the context holds NO clouds (a later
+ * se3icp_run without se3icp_set_cloud returns SE3ICP_ERR_STATE) and se3icp_get_* no longer refer to an earlier run. */
 
 /* a3+a4: exact kNN of every point in its own cloud, ascending by (d2, index).  idx[n*k], d2[n*k] */
 int se3icp_knn(se3icp_ctx* ctx, const double* xyz, size_t n, int k, int32_t* idx, double* d2);

@@ -42,7 +42,7 @@ void ref_default_params(ref_params* p) {
     p->max_num_iterations = reg.max_num_iterations_;
     p->max_num_se3_iterations = reg.max_num_se3_iterations_;
     p->number_of_nn_for_LRF = reg.number_of_nn_for_LRF_;
-    p->trim_keep_largest = 0;
+    p->trim_keep_largest = 1;
     p->mse = reg.mse_;
     p->mse_switch_error = reg.mse_switch_error_;
     p->estimated_overlap = reg.estimated_overlap_;

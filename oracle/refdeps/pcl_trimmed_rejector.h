@@ -5,9 +5,10 @@
 // from its published behaviour: keep int(float(N) * overlap_ratio) correspondences selected with std::nth_element on
 // the float distance; when that count is >= N the input passes through unchanged, in its original order.
 //
-// The direction of PCL's comparator cannot be checked offline; `trim_keep_largest()` selects it,
-// default 0 = keep the smallest distances, the same default and the same switch as oracle/se3icp_oracle.cpp and
-// include/se3icp.h.  Equal distances at the cut resolve to the smaller query index (nth_element leaves that open).
+// PCL passes pcl::isBetterCorrespondence to nth_element, and that comparator is `pc1.distance > pc2.distance`
+// (pcl/correspondence.h), so the LARGEST distances survive.  That source is not in this image, so the direction is
+// restated, not verified: `trim_keep_largest()` selects it, default 1 = PCL's comparator, the same
+// default and the same switch as oracle/se3icp_oracle.cpp and include/se3icp.h.  Equal distances at the cut resolve to the smaller query index (nth_element leaves that open).
 #pragma once
 #include <algorithm>
 #include <vector>
@@ -18,7 +19,7 @@ namespace pcl {
 namespace registration {
 
 inline int& trim_keep_largest() {
-    static int flag = 0;
+    static int flag = 1;
     return flag;
 }
 

@@ -1133,7 +1133,7 @@ void orc_default_params(orc_params* p) {  // reference ctor .cpp:334-348
     p->number_of_nn_for_LRF = 30;
     p->knn_normals_pt2pl = 30;
     p->knn_normals_gicp = 20;
-    p->trim_keep_largest = 0;
+    p->trim_keep_largest = 1;
     p->mse = 0.00001;
     p->mse_switch_error = 0.001;
     p->estimated_overlap = 1.0;

@@ -49,7 +49,7 @@ typedef struct orc_params {
     int32_t number_of_nn_for_LRF;     /* 30 */
     int32_t knn_normals_pt2pl;        /* 30: Open3D EstimateNormals() default */
     int32_t knn_normals_gicp;         /* 20: reference .cpp:43 */
-    int32_t trim_keep_largest;        /* 0: keep smallest distances (documented intent of PCL) */
+    int32_t trim_keep_largest;        /* 1 (default): PCL's isBetterCorrespondence (distance >) keeps the largest; 0: smallest */
     double mse;                       /* 1e-5 */
     double mse_switch_error;          /* 1e-3 */
     double estimated_overlap;         /* 1.0 */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libse3icp_cuda.so")
 
 PT2PT, PT2PL, GICP = 0, 1, 2
 RUN_ICP, RUN_SE3_ICP, RUN_SE3_ICP_CF, RUN_SE3_PURE = 0, 1, 2, 3
-NN_AUTO, NN_BRUTE_F32, NN_EXACT_F64, NN_TREE, NN_TENSOR = 0, 1, 2, 3, 4
+NN_AUTO, NN_BRUTE_F32, NN_EXACT_F64, NN_TREE = 0, 1, 2, 3
 SOURCE, TARGET = 0, 1
 STAGE_NN_SE3, STAGE_NN_XYZ, STAGE_REDUCE, STAGE_KNN_TARGET = 0, 1, 2, 3
 VARIANTS = {"pt2pt": PT2PT, "pt2pl": PT2PL, "gicp": GICP}

@@ -53,8 +53,13 @@ int DeviceBuf::ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
         return SE3ICP_ERR_CUDA;
     }
     if (ptr && keep) {
-        cudaMemcpyAsync(np, ptr, keep, cudaMemcpyDeviceToDevice, st);
-        cudaStreamSynchronize(st);
+        e = cudaMemcpyAsync(np, ptr, keep, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(np);
+            set_last_error("growing a device buffer: copy of %zu bytes -> %s", keep, cudaGetErrorString(e));
+            return SE3ICP_ERR_CUDA;
+        }
     }
     release();
     ptr = np;
@@ -451,7 +456,7 @@ void se3icp_default_params(se3icp_params* p) {  // reference ctor .cpp:334-348
     p->number_of_nn_for_LRF = 30;
     p->knn_normals_pt2pl = 30;
     p->knn_normals_gicp = 20;
-    p->trim_keep_largest = 0;
+    p->trim_keep_largest = 1;  /* PCL's comparator (pc1.distance > pc2.distance): see se3icp.h */
     p->mse = 0.00001;
     p->mse_switch_error = 0.001;
     p->estimated_overlap = 1.0;
@@ -527,8 +532,18 @@ int se3icp_synchronize(se3icp_ctx* c) {
     return SE3ICP_OK;
 }
 
+// entry points that would reallocate or overwrite what an enqueued run still uses
+#define SE3_NOT_PENDING(name)                                                     \
+    do {                                                                          \
+        if (c->run_pending) {                                                     \
+            set_last_error(name ": a run is pending (call se3icp_run_finish)");   \
+            return SE3ICP_ERR_STATE;                                              \
+        }                                                                         \
+    } while (0)
+
 int se3icp_set_cloud(se3icp_ctx* c, int which, const double* xyz, size_t n, int append) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("se3icp_set_cloud");
     if ((which != SE3ICP_SOURCE && which != SE3ICP_TARGET) || (!xyz && n > 0)) {
         set_last_error("se3icp_set_cloud: bad argument");
         return SE3ICP_ERR_ARG;
@@ -552,6 +567,7 @@ int se3icp_set_cloud(se3icp_ctx* c, int which, const double* xyz, size_t n, int 
 
 int se3icp_set_cloud_device(se3icp_ctx* c, int which, const double* d_xyz, size_t n) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("se3icp_set_cloud_device");
     if ((which != SE3ICP_SOURCE && which != SE3ICP_TARGET) || !d_xyz || n == 0) return SE3ICP_ERR_ARG;
     c->raw_view[which] = d_xyz;
     c->n[which] = n;
@@ -561,10 +577,7 @@ int se3icp_set_cloud_device(se3icp_ctx* c, int which, const double* d_xyz, size_
 
 int se3icp_swap_clouds(se3icp_ctx* c) {
     SE3_TRY(check_ctx(c));
-    if (c->run_pending) {
-        set_last_error("se3icp_swap_clouds: a run is pending");
-        return SE3ICP_ERR_STATE;
-    }
+    SE3_NOT_PENDING("se3icp_swap_clouds");
     c->raw[0].swap(c->raw[1]);
     std::swap(c->raw_view[0], c->raw_view[1]);
     std::swap(c->n[0], c->n[1]);
@@ -590,6 +603,7 @@ int se3icp_run_async(se3icp_ctx* c, const se3icp_params* p) {
 
 static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     if (!p) return SE3ICP_ERR_ARG;
+    SE3_NOT_PENDING("se3icp_run_async");
     if (c->n[0] == 0 || c->n[1] == 0 || !c->raw_view[0] || !c->raw_view[1]) {
         set_last_error("source/target cloud not set");
         return SE3ICP_ERR_STATE;
@@ -599,9 +613,9 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
         set_last_error("kNN sizes above %d are not supported", SE3ICP_MAX_KNN);
         return SE3ICP_ERR_UNSUPPORTED;
     }
-    if (p->nn_mode == SE3ICP_NN_TENSOR) {
-        set_last_error("SE3ICP_NN_TENSOR is not built (the pruned traversal made the brute-force sweep moot)");
-        return SE3ICP_ERR_UNSUPPORTED;
+    if (p->nn_mode < SE3ICP_NN_AUTO || p->nn_mode > SE3ICP_NN_TREE) {
+        set_last_error("bad nn_mode %d", p->nn_mode);
+        return SE3ICP_ERR_ARG;
     }
     SE3_TRY(fill_config(c, p));
     SE3_TRY(alloc_run(c));
@@ -986,6 +1000,21 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
 // ================================================================================================
 namespace {
 
+// The stage-level entry points borrow the context's cloud slots, feature planes and iteration state as scratch.
+// Whatever clouds the context held are gone afterwards: the scope guard marks them unset, so a later se3icp_run
+// without a fresh se3icp_set_cloud fails with SE3ICP_ERR_STATE instead of reading half-overwritten buffers.
+struct StageScope {
+    se3icp_ctx* c;
+    ~StageScope() {
+        for (int w = 0; w < 2; w++) {
+            c->n[w] = 0;
+            c->raw_view[w] = nullptr;
+            c->feat[w].valid = false;
+        }
+        c->src_index_built = false;
+    }
+};
+
 int upload_cloud_and_index(se3icp_ctx* c, int w, const double* xyz, size_t n) {
     SE3_TRY(se3icp_set_cloud(c, w, xyz, n, 0));
     SE3_TRY(c->index[w].reserve((int)n));
@@ -1093,6 +1122,8 @@ int stage_corr_alloc(se3icp_ctx* c, size_t n) {
 
 int se3icp_knn(se3icp_ctx* c, const double* xyz, size_t n, int k, int32_t* idx, double* d2) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!idx) return SE3ICP_ERR_ARG;
     SE3_TRY(stage_features(c, xyz, n, 0, 0, k, true));
     const double* dd = c->scratch.as<double>();
@@ -1105,6 +1136,8 @@ int se3icp_knn(se3icp_ctx* c, const double* xyz, size_t n, int k, int32_t* idx, 
 
 int se3icp_lrf(se3icp_ctx* c, const double* xyz, size_t n, int k, double* frames) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!frames) return SE3ICP_ERR_ARG;
     SE3_TRY(stage_features(c, xyz, n, k, 0, k, false));
     std::vector<double> rows(9 * n);
@@ -1123,6 +1156,8 @@ int se3icp_lrf(se3icp_ctx* c, const double* xyz, size_t n, int k, double* frames
 
 int se3icp_normals(se3icp_ctx* c, const double* xyz, size_t n, int k, double* normals) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!normals) return SE3ICP_ERR_ARG;
     SE3_TRY(stage_features(c, xyz, n, 0, k, k, false));
     return download_planes(c, c->nrm[0], normals, n, 3);
@@ -1130,6 +1165,8 @@ int se3icp_normals(se3icp_ctx* c, const double* xyz, size_t n, int k, double* no
 
 int se3icp_gicp_cov(se3icp_ctx* c, const double* normals, size_t n, double eps, double* cov) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!normals || !cov || n == 0) return SE3ICP_ERR_ARG;
     SE3_TRY(upload_planes(c, c->nrm[0], normals, n, 3, 3, 0));
     SE3_TRY(c->cov[0].ensure(6 * n * sizeof(double)));
@@ -1149,6 +1186,8 @@ int se3icp_gicp_cov(se3icp_ctx* c, const double* normals, size_t n, double eps, 
 int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double* tgt_rows, size_t m, int nn_mode,
                   int32_t* idx, double* d2, int64_t* exact_repairs) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!src_rows || !tgt_rows || !idx || n == 0 || m == 0) return SE3ICP_ERR_ARG;
     // target: spatial order from the translation part, rotation planes as given (alpha = beta = 1)
     std::vector<double> xyz(3 * m);
@@ -1203,6 +1242,8 @@ int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double*
 int se3icp_nn_xyz(se3icp_ctx* c, const double* queries, size_t n, const double* tgt_xyz, size_t m, int32_t* idx,
                   double* d2) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!queries || !tgt_xyz || !idx || n == 0 || m == 0) return SE3ICP_ERR_ARG;
     SE3_TRY(upload_cloud_and_index(c, 1, tgt_xyz, m));
     SE3_TRY(upload_planes(c, c->scratch, queries, n, 3, 3, 0));
@@ -1231,6 +1272,8 @@ int se3icp_nn_xyz(se3icp_ctx* c, const double* queries, size_t n, const double* 
 int se3icp_trim(se3icp_ctx* c, const float* dist, size_t n, double overlap, int keep_largest, uint8_t* keep,
                 int64_t* n_keep) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!dist || !keep || n == 0) return SE3ICP_ERR_ARG;
     SE3_TRY(stage_state(c));
     SE3_TRY(stage_corr_alloc(c, n));
@@ -1317,6 +1360,8 @@ int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* sr
 int se3icp_reduce_pt2pt(se3icp_ctx* c, const double* src, size_t n, const double* tgt, size_t m, const int32_t* corr_tgt,
                         double* T_out) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!T_out) return SE3ICP_ERR_ARG;
     return stage_reduce(c, SE3ICP_PT2PT, src, nullptr, n, tgt, nullptr, nullptr, m, corr_tgt, nullptr, nullptr, nullptr, T_out);
 }
@@ -1324,6 +1369,8 @@ int se3icp_reduce_pt2pt(se3icp_ctx* c, const double* src, size_t n, const double
 int se3icp_reduce_pt2pl(se3icp_ctx* c, const double* src, size_t n, const double* tgt, const double* tgt_normals, size_t m,
                         const int32_t* corr_tgt, double* out27) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!tgt_normals || !out27) return SE3ICP_ERR_ARG;
     return stage_reduce(c, SE3ICP_PT2PL, src, nullptr, n, tgt, tgt_normals, nullptr, m, corr_tgt, nullptr, nullptr, out27,
                         nullptr);
@@ -1333,6 +1380,8 @@ int se3icp_reduce_gicp(se3icp_ctx* c, const double* src, const double* src_cov, 
                        const double* tgt_cov, size_t m, const int32_t* corr_tgt, const double* conf_src,
                        const double* conf_tgt, double* out27) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!src_cov || !tgt_cov || !out27) return SE3ICP_ERR_ARG;
     return stage_reduce(c, SE3ICP_GICP, src, src_cov, n, tgt, nullptr, tgt_cov, m, corr_tgt, conf_src, conf_tgt, out27,
                         nullptr);
@@ -1340,6 +1389,8 @@ int se3icp_reduce_gicp(se3icp_ctx* c, const double* src, const double* src_cov, 
 
 int se3icp_solve(se3icp_ctx* c, const double* in27, double* T_out) {
     SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
     if (!in27 || !T_out) return SE3ICP_ERR_ARG;
     SE3_TRY(stage_state(c));
     SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));

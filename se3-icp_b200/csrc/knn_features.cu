@@ -96,6 +96,39 @@ __device__ __forceinline__ void list_at(const key_t (&Ld)[4], const int (&Li)[4]
     i = __shfl_sync(SE3_FULL, si, e & 31);
 }
 
+// Rare path of shrink_pool(): the bisection on the distance VALUE cannot separate candidates that tie at the
+// threshold (hundreds of coincident points, e.g. invalid-depth pixels mapped to one xyz).  The pool is then cut to
+// exactly the K smallest by (distance, original index) — the order the final list uses — so it stays bounded.
+// Not inlined: keeps the second copy of the merge network out of the hot kernel's register budget.
+__device__ __noinline__ double knn_exact_trim(unsigned long long* pd, int* pi, int pool, int K, int lane) {
+    key_t Ld[4] = {kInfKey, kInfKey, kInfKey, kInfKey};
+    int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int base = 0; base < pool; base += 32) {
+        int t = base + lane;
+        key_t cd = kInfKey;
+        int ci = 0x7fffffff;
+        if (t < pool) {
+            cd = pd[t];
+            ci = pi[t];
+        }
+        merge32(Ld, Li, cd, ci, lane);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int j = lane + 32 * t;
+        if (j < K) {
+            pd[j] = Ld[t];
+            pi[j] = Li[t];
+        }
+    }
+    key_t kd;
+    int ki;
+    list_at(Ld, Li, K - 1, kd, ki);
+    __syncwarp();
+    return __longlong_as_double((long long)kd);
+}
+
 __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIndex I, FeatureArgs fa) {
     extern __shared__ __align__(16) unsigned char knn_smem[];  // dynamic: more than 48 KB from 12 warps per block on
     KnnScratch* scratch = reinterpret_cast<KnnScratch*>(knn_smem);
@@ -173,6 +206,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         pool = out;
         tau = hi;
         __syncwarp();
+        if (pool > K + 24) {  // ties at the threshold (pool >= K holds, so the K-th entry exists)
+            tau = knn_exact_trim(W.d, W.id, pool, K, lane);
+            pool = K;
+        }
     };
     auto eval_leaf = [&](int leaf) {
         int p = leaf * 32 + lane;

@@ -35,7 +35,9 @@ void report(const char* where, int rc) {
 // The reference's drivers build a fresh IterativeSE3Registration per pair (benchmark_kitti.cpp:128).  Creating a
 // CUDA context object (stream, pinned buffers, device allocations) costs ~40 ms, a registration of a small cloud
 // ~3 ms, so contexts are recycled through a process-wide pool: a destroyed object parks its context (with its
-// grown device buffers) and the next object on the same device picks it up.
+// grown device buffers) and the next object on the same device picks it up.  At most SE3ICP_POOL_CONTEXTS (default 4)
+// contexts are parked; the pool never calls CUDA from its static destructor (the runtime may already be unloading at
+// process exit, and the driver reclaims everything anyway).
 class ContextPool {
 public:
     se3icp_ctx* acquire(int device) {
@@ -59,16 +61,19 @@ public:
     void release(int device, se3icp_ctx* c) {
         if (!c) return;
         std::lock_guard<std::mutex> lock(mu_);
-        if (free_.size() < 16)
+        if (free_.size() < capacity_)
             free_.emplace_back(device, c);
         else
             se3icp_destroy(c);
     }
-    ~ContextPool() {
-        for (auto& f : free_) se3icp_destroy(f.second);
+    ContextPool() {
+        const char* e = std::getenv("SE3ICP_POOL_CONTEXTS");
+        if (e && *e) capacity_ = (size_t)std::max(0, std::atoi(e));
     }
+    ~ContextPool() = default;  // parked contexts are left to process teardown on purpose (see above)
 
 private:
+    size_t capacity_ = 4;
     std::mutex mu_;
     std::vector<std::pair<int, se3icp_ctx*>> free_;
 };
@@ -115,6 +120,39 @@ IterativeSE3Registration::IterativeSE3Registration()  // defaults of the referen
 }
 
 IterativeSE3Registration::~IterativeSE3Registration() { pool().release(device_, ctx_); }
+
+IterativeSE3Registration::IterativeSE3Registration(const IterativeSE3Registration& o) : IterativeSE3Registration() { *this = o; }
+
+IterativeSE3Registration& IterativeSE3Registration::operator=(const IterativeSE3Registration& o) {
+    if (this == &o) return *this;
+    max_num_iterations_ = o.max_num_iterations_;
+    max_num_se3_iterations_ = o.max_num_se3_iterations_;
+    number_of_nn_for_LRF_ = o.number_of_nn_for_LRF_;
+    mse_ = o.mse_;
+    mse_switch_error_ = o.mse_switch_error_;
+    estimated_overlap_ = o.estimated_overlap_;
+    alpha_rot = o.alpha_rot;
+    beta_transl = o.beta_transl;
+    scale_preprocessing = o.scale_preprocessing;
+    lrf_radius_ = o.lrf_radius_;
+    current_estimated_T_ = o.current_estimated_T_;
+    num_iterations_ = o.num_iterations_;
+    num_pure_se3_iterations_ = o.num_pure_se3_iterations_;
+    time_se3_correspondence_search_ = o.time_se3_correspondence_search_;
+    time_before_pure_icp_ = o.time_before_pure_icp_;
+    estimated_history_ = o.estimated_history_;
+    source_ = o.source_;
+    source_moving_ = o.source_moving_;
+    target_ = o.target_;
+    source_se3_cloud_ = o.source_se3_cloud_;
+    target_se3_cloud_ = o.target_se3_cloud_;
+    current_correspondences_set = o.current_correspondences_set;
+    current_correspondences_set_pcl.reset(new pcl::Correspondences(*o.current_correspondences_set_pcl));
+    mirror_state_ = o.mirror_state_;
+    trim_keep_largest_ = o.trim_keep_largest_;
+    set_device(o.device_);  // the GPU context is not shared: this object acquires its own on first use
+    return *this;
+}
 
 void IterativeSE3Registration::set_device(int device) {
     if (ctx_ && device != device_) {
@@ -257,7 +295,7 @@ void IterativeSE3Registration::run_entry(int entry, const std::string& variant_n
     p.max_num_iterations = max_num_iterations_;
     p.max_num_se3_iterations = max_num_se3_iterations_;
     p.number_of_nn_for_LRF = number_of_nn_for_LRF_;
-    p.trim_keep_largest = trim_keep_largest_ ? 1 : 0;
+    p.trim_keep_largest = trim_keep_largest_ ? 1 : 0;  // default: PCL's comparator (keep largest)
     p.mse = mse_;
     p.mse_switch_error = mse_switch_error_;
     p.estimated_overlap = estimated_overlap_;
@@ -290,6 +328,23 @@ void IterativeSE3Registration::run_entry(int entry, const std::string& variant_n
     }
     if (mirror_state_) {
         size_t n = source_.points_.size(), m = target_.points_.size();
+        // clouds as the reference leaves them: run_icp transforms source_moving_ only (.cpp:541); the SE(3) entries
+        // first centre and scale all three clouds in place (.cpp:568-582), then move source_moving_ (.cpp:706)
+        Eigen::Matrix4d T_work = current_estimated_T_;
+        if (entry != SE3ICP_RUN_ICP) {
+            const double s = st.scaling_factor;
+            const Eigen::Vector3d cs = source_.GetCenter(), ct = target_.GetCenter();
+            const Eigen::Matrix3d R = current_estimated_T_.block<3, 3>(0, 0);
+            const Eigen::Vector3d t = current_estimated_T_.block<3, 1>(0, 3);
+            T_work.block<3, 1>(0, 3) = (t + R * cs - ct) * s;  // inverse of the un-normalisation at .cpp:735-738
+            source_.Translate(-cs);
+            source_moving_.Translate(-cs);
+            target_.Translate(-ct);
+            source_.Scale(s, Eigen::Vector3d(0, 0, 0));
+            source_moving_.Scale(s, Eigen::Vector3d(0, 0, 0));
+            target_.Scale(s, Eigen::Vector3d(0, 0, 0));
+        }
+        source_moving_.Transform(T_work);
         std::vector<int> idx(n);
         std::vector<double> dist(n);
         if (se3icp_get_correspondences(c, idx.data(), dist.data(), n) == SE3ICP_OK) store_correspondences(idx, dist);

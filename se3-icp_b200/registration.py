@@ -32,7 +32,7 @@ class IterativeSE3Registration:
         self.current_estimated_T_ = np.eye(4)
         self.estimated_history_ = []
         # extensions (not in the reference): comparator direction of the trimmed rejector and NN strategy
-        self.trim_keep_largest_ = False
+        self.trim_keep_largest_ = True  # PCL 1.14's comparator (include/se3icp.h)
         self.nn_mode_ = capi.NN_AUTO
         self._source = np.zeros((0, 3))
         self._target = np.zeros((0, 3))

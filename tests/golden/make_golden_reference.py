@@ -33,13 +33,20 @@ def cases():
     out["c1_se3_pt2pl_trim80"] = dict(cloud=("c1", {}), entry="se3", variant="pt2pl", params=dict(estimated_overlap=0.8))
     out["c1_se3_gicp_trim70_largest"] = dict(cloud=("c1", {}), entry="se3", variant="gicp",
                                              params=dict(estimated_overlap=0.7, trim_keep_largest=1))
+    out["c1_se3_gicp_trim70_smallest"] = dict(cloud=("c1", {}), entry="se3", variant="gicp",
+                                              params=dict(estimated_overlap=0.7, trim_keep_largest=0))
     out["c1_se3_pt2pt_alpha1_knn60"] = dict(cloud=("c1", {}), entry="se3", variant="pt2pt",
                                             params=dict(alpha_rot=1.0, beta_transl=2.0, number_of_nn_for_LRF=60,
                                                         scale_preprocessing=2.0))
-    for level, seed in (("easy", 1), ("moderate", 2)):
+    # easy: trimmed with PCL's comparator (the default); moderate: trimmed keeping the smallest distances.
+    # (With the default comparator the moderate pt2pl problem exhausts its 150 iterations without converging; such a
+    # run is chaotic — the oracle's own OpenMP summation order moves the result by 1e-3 rad from run to run — so it
+    # cannot serve as a golden vector.)
+    for level, seed, largest in (("easy", 1, 1), ("moderate", 2, 0)):
         for v in ("pt2pt", "pt2pl", "gicp"):
             out["bunny_%s_%s" % (level, v)] = dict(cloud=("bunny", dict(level=level, seed=seed, n_points=3000)), entry="se3",
-                                                   variant=v, params=dict(number_of_nn_for_LRF=90, estimated_overlap=0.9))
+                                                   variant=v, params=dict(number_of_nn_for_LRF=90, estimated_overlap=0.9,
+                                                                          trim_keep_largest=largest))
     out["lidar_small_se3_gicp"] = dict(cloud=("lidar", dict(seed=3, n_rings=32, n_az=400)), entry="se3", variant="gicp",
                                        params=dict(W.KITTI_PARAMS))
     out["rgbd_small_cf"] = dict(cloud=("rgbd", dict(seed=1, stride=6)), entry="cf", variant="gicp", params=dict(W.LOUNGE_PARAMS))

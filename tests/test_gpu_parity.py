@@ -51,6 +51,30 @@ def test_knn_bunny_full(ctx, orc):
     np.testing.assert_array_equal(gi, oi)
 
 
+@pytest.mark.parametrize("n_dup,k", [(230, 90), (600, 90), (300, 128), (260, 20)])
+def test_knn_many_coincident_points(ctx, orc, n_dup, k):
+    """Hundreds of coincident points (invalid-depth pixels mapped to one xyz): every candidate ties at the search
+    radius, so the bisection on the distance value cannot shrink the per-warp pool; the exact (distance, index) trim
+    must keep it bounded and the result must still be the oracle's list (ties -> smaller index)."""
+    rng = np.random.default_rng(n_dup)
+    base = rng.normal(size=(700, 3))
+    dup = np.repeat(np.array([[0.25, -0.5, 0.125]]), n_dup, axis=0)
+    ring = np.array([0.25, -0.5, 0.125]) + 0.5 * np.eye(3)[rng.integers(0, 3, 200)] * rng.choice([-1.0, 1.0], (200, 1))
+    pts = np.concatenate([base, dup, ring])[rng.permutation(700 + n_dup + 200)]
+    gi, gd = ctx.knn(pts, k)
+    oi, od = orc.knn_self(pts, k)
+    np.testing.assert_array_equal(gd, od)
+    np.testing.assert_array_equal(gi, oi)
+    # the feature pass over such neighbourhoods must run through as well; away from the coincident cluster (whose
+    # scatter matrix is exactly zero, so its eigenvectors are arbitrary) the frames agree with the oracle
+    gf = ctx.lrf(pts, k)[:, :3, :3]
+    of = orc.toldi(pts, k)[:, :3, :3]
+    far = np.linalg.norm(pts - np.array([0.25, -0.5, 0.125]), axis=1) > 1.5
+    ok = far & np.isfinite(of).all(axis=(1, 2))
+    assert ok.sum() > 50
+    np.testing.assert_allclose(gf[ok], of[ok], atol=1e-9)
+
+
 def test_knn_edge_cases(ctx, orc, capi):
     rng = np.random.default_rng(0)
     for n in (1, 2, 31, 32, 33, 100):
@@ -391,6 +415,25 @@ def test_kitti_scale_properties(ctx, orc, capi):
     assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold["kitti_it"])
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("config", ["kitti", "lounge"])
+def test_fullsize_extra_seeds(ctx, capi, config, seed):
+    """configs[2] / configs[3] at full size on two more seeds, against the committed oracle goldens."""
+    gold = np.load(os.path.join(W.GOLDEN, "fullsize_oracle.npz"))
+    if config == "kitti":
+        src, tgt, _ = W.lidar_pair(seed=seed)
+        p = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, **W.KITTI_PARAMS)
+    else:
+        src, tgt, _ = W.rgbd_pair(seed=seed)
+        p = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP_CF, **W.LOUNGE_PARAMS)
+    assert list(gold["%s_n_s%d" % (config, seed)]) == [len(src), len(tgt)]
+    ctx.set_cloud(capi.SOURCE, src)
+    ctx.set_cloud(capi.TARGET, tgt)
+    Tg, sg = ctx.run(p)
+    assert_transform_parity(Tg, gold["%s_T_s%d" % (config, seed)], tgt)
+    assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold["%s_it_s%d" % (config, seed)])
+
+
 def test_lounge_scale_with_cf(ctx, orc, capi):
     """BASELINE.json configs[3]: lounge-like RGB-D pair, se3_gicp_with_cf (benchmark_lounge.cpp:183-186).
     Parity against the oracle on the stride-4 image (15 k points); at full resolution (~250 k points) the
@@ -408,7 +451,8 @@ def test_lounge_scale_with_cf(ctx, orc, capi):
     assert list(gold["lounge_n"]) == [len(src), len(tgt)]
     assert_transform_parity(Tg, gold["lounge_T"], tgt)
     assert [sg.num_iterations, sg.num_pure_se3_iterations] == list(gold["lounge_it"])
-    assert np.degrees(rot_err(Tg, T_gt)) < 1.0 and np.linalg.norm(Tg[:3, 3] - T_gt[:3, 3]) < 0.15  # what the method reaches here
+    # what the method reaches here with PCL's trimmed comparator (the default); benchmark_synthetic.cpp:410 asks for 2 deg
+    assert np.degrees(rot_err(Tg, T_gt)) < 2.0 and np.linalg.norm(Tg[:3, 3] - T_gt[:3, 3]) < 0.15
     assert sg.time_se3_correspondence_search_ms > 0 and sg.time_before_pure_icp_ms >= sg.time_se3_correspondence_search_ms
 
 
