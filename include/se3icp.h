@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SE3ICP_ABI_VERSION 2
+#define SE3ICP_ABI_VERSION 3
 
 enum se3icp_status {
     SE3ICP_OK = 0,
@@ -105,6 +105,9 @@ typedef struct se3icp_stats {
     int64_t feature_reuses;          /* clouds whose neighbourhood features were taken from an earlier run (0, 1 or 2) */
     int64_t queries_searched;        /* nearest-neighbour queries that ran a tree search, summed over the iterations; the
                                         rest (iterations x source points - this) were settled by the coherence filter */
+    int64_t graph_instantiations;    /* loop-graph executables this context has created so far (it keeps one and
+                                        re-parameterises it from run to run; a count that grows with the runs means the
+                                        launch sequence keeps changing) */
 } se3icp_stats;
 
 typedef struct se3icp_ctx se3icp_ctx;

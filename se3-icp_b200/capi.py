@@ -68,6 +68,7 @@ class Stats(C.Structure):
         ("time_se3_phase_search_ms", C.c_double),
         ("feature_reuses", C.c_int64),
         ("queries_searched", C.c_int64),
+        ("graph_instantiations", C.c_int64),
     ]
 
 

@@ -121,6 +121,11 @@ CorrBuffers se3icp_ctx::corr_buffers(bool with_d2) const {
     cb.work = work.as<int>();
     cb.ref_q = ref_q.as<double>();
     cb.ref_d2nd = ref_d2nd.as<double>();
+    // single-launch trimmed rejection whenever no cross-rank histogram exchange is needed
+    const bool thr_trim = cfg.trim_active && cfg.n_keep_target > 0 && !sharded;
+    cb.thist = thr_trim ? thist.as<unsigned int>() : nullptr;
+    cb.tcand = tcand.as<unsigned long long>();
+    cb.tcount = tcount.as<unsigned int>();
     return cb;
 }
 
@@ -204,6 +209,11 @@ int alloc_run(se3icp_ctx* c) {
     SE3_TRY(c->partials.ensure((size_t)kReduceBlocks * kReducePartials * sizeof(double)));
     SE3_TRY(c->hist.ensure(4 * 256 * sizeof(unsigned int)));
     SE3_TRY(c->block_eq.ensure((size_t)kReduceBlocks * sizeof(int)));
+    SE3_TRY(c->tcount.ensure(kTcountWords * sizeof(unsigned int)));
+    if (cfg.trim_active) {
+        SE3_TRY(c->thist.ensure((size_t)kTrimHistBins * sizeof(unsigned int)));
+        SE3_TRY(c->tcand.ensure(N * sizeof(unsigned long long)));
+    }
     if (cfg.record_history) SE3_TRY(c->history.ensure((size_t)cfg.max_history * 16 * sizeof(double)));
     SE3_TRY(c->state.ensure(sizeof(IterState)));
     SE3_TRY(c->totals.ensure(kReducePartials * sizeof(double)));
@@ -334,6 +344,8 @@ int enqueue_setup(se3icp_ctx* c) {
     SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, (size_t)N * sizeof(int), st));
     if (cfg.coherence || cfg.coherence_xyz) SE3_CUDA(cudaMemsetAsync(c->ref_d2nd.ptr, 0xff, (size_t)N * sizeof(double), st));  // NaN: not known
     if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
+    SE3_CUDA(cudaMemsetAsync(c->tcount.ptr, 0, kTcountWords * sizeof(unsigned int), st));
+    if (cfg.trim_active) SE3_CUDA(cudaMemsetAsync(c->thist.ptr, 0, (size_t)kTrimHistBins * sizeof(unsigned int), st));
     SE3_TRY(launch_mark_loop_start(ds, st));
     c->launches += 1;
     return 0;
@@ -367,8 +379,9 @@ int enqueue_iteration(se3icp_ctx* c, unsigned long long cond_handle = 0) {
     if (multi && !nccl) return SE3ICP_ERR_NCCL;
     ncclComm_t comm = (ncclComm_t)c->comm;
     if (cfg.trim_active && cfg.n_keep_target > 0) {
-        if (!c->sharded) {
-            SE3_TRY(launch_trim(cfg, ds, cb, S.n, c->hist.as<unsigned int>(), c->block_eq.as<int>(), st));
+        if (cb.thist) {
+            SE3_TRY(launch_trim_select(cfg, ds, cb, S.begin, S.end, st));
+            c->launches += 2;
         } else {
             // global threshold: every radix pass all-reduces its 256-bin histogram; ties at the
             // threshold are granted in global index order (lower ranks first)
@@ -387,20 +400,23 @@ int enqueue_iteration(se3icp_ctx* c, unsigned long long cond_handle = 0) {
                 rank_eq = c->rank_eq.as<int>();
             }
             SE3_TRY(launch_trim_apply(cfg, ds, df, nl, hist, c->block_eq.as<int>(), rank_eq, c->comm_rank, cb.keep + S.begin, st));
+            c->launches += 6;
         }
-        c->launches += 6;
     }
-    SE3_TRY(launch_reduce(S, T, cfg, ds, cb, c->partials.as<double>(), st));
+    // single GPU: the last block of the reduction also solves, updates and decides (an iteration ends with this launch)
+    SolveFusion fuse{};
+    fuse.enabled = !multi;
+    fuse.history = c->history.as<double>();
+    fuse.hist = cb.thist ? nullptr : c->hist.as<unsigned int>();
+    fuse.cond_handle = cond_handle;
+    SE3_TRY(launch_reduce(S, T, cfg, ds, cb, c->partials.as<double>(), fuse, st));
+    c->launches += 1;
     if (multi) {
         // one all-reduce of the 29-double record per iteration; every rank then runs the identical solve
         SE3_TRY(launch_sum_partials(c->partials.as<double>(), c->totals.as<double>(), st));
         SE3_NCCL(nccl->AllReduce(c->totals.ptr, c->totals.ptr, kReducePartials, ncclFloat64, ncclSum, comm, st));
         SE3_TRY(launch_solve_update(cfg, ds, c->totals.as<double>(), 1, c->history.as<double>(), c->hist.as<unsigned int>(),
                                     cond_handle, st));
-        c->launches += 3;
-    } else {
-        SE3_TRY(launch_solve_update(cfg, ds, c->partials.as<double>(), kReduceBlocks, c->history.as<double>(),
-                                    c->hist.as<unsigned int>(), cond_handle, st));
         c->launches += 2;
     }
     return 0;
@@ -427,6 +443,66 @@ void release_loop_graph(se3icp_ctx* c) {
     if (c->loop_graph) cudaGraphDestroy(c->loop_graph);
     c->loop_exec = nullptr;
     c->loop_graph = nullptr;
+}
+
+// The loop graph of a run: a conditional WHILE node whose body is the captured iteration.  Capturing costs ~10 us;
+// instantiating ~100 us (measured, profiles/experiments/cond_update_test.cu), so the executable graph is kept by the
+// context and only re-parameterised (cudaGraphExecUpdate, ~3 us) from the freshly captured one — pointers, sizes and
+// grids differ from pair to pair, the topology does not.  It is re-instantiated when the update is refused (another
+// launch sequence: trimming switched on or off, another search mode).
+int build_loop_graph(se3icp_ctx* c) {
+    cudaGraph_t graph = nullptr;
+    SE3_CUDA(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle handle;
+    cudaGraphNodeParams np = {};
+    cudaGraphNode_t node;
+    cudaError_t e = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+    if (e == cudaSuccess) {
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        e = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamBeginCaptureToGraph(c->stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                          cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        SE3_CUDA(e);
+    }
+    long long before = c->launches;
+    int rc = enqueue_iteration(c, (unsigned long long)handle);  // the last block of reduce_kernel sets the loop condition
+    cudaGraph_t captured = nullptr;
+    e = cudaStreamEndCapture(c->stream, &captured);
+    c->launches_per_iter = c->launches - before;
+    c->launches = before;
+    if (rc || e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        if (rc) return rc;
+        SE3_CUDA(e);
+    }
+    if (c->loop_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(c->loop_exec, graph, &info) != cudaSuccess) {
+            cudaGetLastError();  // not an error of the run: fall back to a fresh executable
+            cudaGraphExecDestroy(c->loop_exec);
+            c->loop_exec = nullptr;
+        } else {
+            c->graph_updates += 1;
+        }
+    }
+    if (!c->loop_exec) {
+        e = cudaGraphInstantiate(&c->loop_exec, graph, 0);
+        if (e != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            SE3_CUDA(e);
+        }
+        c->graph_instantiations += 1;
+    }
+    if (c->loop_graph) cudaGraphDestroy(c->loop_graph);
+    c->loop_graph = graph;
+    return 0;
 }
 
 int check_ctx(se3icp_ctx* c) {
@@ -624,34 +700,13 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     SE3_CUDA(cudaEventRecord(c->ev_begin, c->stream));
     SE3_TRY(enqueue_setup(c));
     SE3_CUDA(cudaEventRecord(c->ev_setup, c->stream));
-    // Iterations: the stop/phase decision lives on the device (solve_update).
-    release_loop_graph(c);
+    // Iterations: the stop/phase decision lives on the device (tail of reduce_kernel).
     c->graph_run = false;
     const bool multi_rank = c->sharded && c->comm && c->comm_size > 1;
     if (want_graph(p) && !multi_rank) {
         // The whole loop is ONE graph launch: a conditional WHILE node whose body is the captured iteration;
         // its last kernel sets the condition from the device-side done flag.  The host never round-trips.
-        SE3_CUDA(cudaGraphCreate(&c->loop_graph, 0));
-        cudaGraphConditionalHandle handle;
-        SE3_CUDA(cudaGraphConditionalHandleCreate(&handle, c->loop_graph, 1, cudaGraphCondAssignDefault));
-        cudaGraphNodeParams np = {};
-        np.type = cudaGraphNodeTypeConditional;
-        np.conditional.handle = handle;
-        np.conditional.type = cudaGraphCondTypeWhile;
-        np.conditional.size = 1;
-        cudaGraphNode_t node;
-        SE3_CUDA(cudaGraphAddNode(&node, c->loop_graph, nullptr, 0, &np));
-        cudaGraph_t body = np.conditional.phGraph_out[0];
-        SE3_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-        long long before = c->launches;
-        int rc = enqueue_iteration(c, (unsigned long long)handle);  // solve_update sets the loop condition
-        cudaGraph_t captured = nullptr;
-        cudaError_t ce = cudaStreamEndCapture(c->stream, &captured);
-        if (rc) return rc;
-        SE3_CUDA(ce);
-        c->launches_per_iter = c->launches - before;
-        c->launches = before;
-        SE3_CUDA(cudaGraphInstantiate(&c->loop_exec, c->loop_graph, 0));
+        SE3_TRY(build_loop_graph(c));
         SE3_CUDA(cudaGraphLaunch(c->loop_exec, c->stream));
         c->graph_run = true;
     } else {
@@ -679,17 +734,8 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         set_last_error("no run pending");
         return SE3ICP_ERR_STATE;
     }
-    if (c->blocking_wait) {
-        // ev_end is the last thing enqueued by run_async.  Poll and yield: as responsive as a spin when cores are free,
-        // and the core goes to a thread that is enqueueing when they are not (8 ranks x 8 contexts on one host)
-        cudaError_t q;
-        while ((q = cudaEventQuery(c->ev_end)) == cudaErrorNotReady) std::this_thread::yield();
-        SE3_CUDA(q);
-        SE3_CUDA(cudaStreamSynchronize(c->stream));
-    } else {
-        SE3_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    c->run_pending = false;
+    c->run_pending = false;  // whatever happens below, the context accepts calls again
+    SE3_CUDA(cudaStreamSynchronize(c->stream));
     const IterState& hs = *c->h_state;
     if (T_out) memcpy(T_out, hs.T_final, 16 * sizeof(double));
     if (stats) {
@@ -709,6 +755,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         stats->kernel_launches = c->launches + (c->graph_run ? c->launches_per_iter * (long long)hs.iter : 0);
         stats->feature_reuses = c->feature_reuses;
         stats->queries_searched = (long long)hs.searched_total;
+        stats->graph_instantiations = c->graph_instantiations;
     }
     return SE3ICP_OK;
 }
@@ -777,47 +824,57 @@ int se3icp_get_se3_cloud(se3icp_ctx* c, int which, double* frames16, size_t n) {
     return SE3ICP_OK;
 }
 
-// ---- batch of independent pairs: one host thread per context, contexts run concurrently on their streams
+// ---- batch of independent pairs: the contexts run concurrently on their streams, fed by at most two host threads.
+// A run is one asynchronous enqueue (set-up kernels + one graph launch), so a thread walks round-robin over its
+// contexts: collect the result of the pair a context finished, hand it the next one.  (Round 1 used one polling
+// thread per context: 16 threads per GPU x 8 ranks fought over the host cores and cost 8 % at 8 GPUs.)
 static int run_batch_impl(se3icp_ctx** ctxs, int n_ctx, int n_pairs, const double* const* src, const size_t* n_src,
                           const double* const* tgt, const size_t* n_tgt, const se3icp_params* p, double* T_out,
                           se3icp_stats* stats, bool device_inputs) {
     if (!ctxs || n_ctx <= 0 || n_pairs < 0 || !src || !tgt || !n_src || !n_tgt || !p || !T_out) return SE3ICP_ERR_ARG;
-    std::vector<int> rc(n_ctx, 0);
-    std::vector<std::string> errs(n_ctx);
-    auto worker = [&](int ci) {
-        se3icp_ctx* c = ctxs[ci];
-        // several host threads per GPU (and one process per GPU next to it): waiting threads yield while they poll
-        // the end event, so the cores stay available to the threads that are enqueueing
-        c->blocking_wait = n_ctx > 1;
-        for (int pi = ci; pi < n_pairs; pi += n_ctx) {
-            int r;
-            if (device_inputs) {
-                r = se3icp_set_cloud_device(c, SE3ICP_SOURCE, src[pi], n_src[pi]);
-                if (!r) r = se3icp_set_cloud_device(c, SE3ICP_TARGET, tgt[pi], n_tgt[pi]);
-            } else {
-                r = se3icp_set_cloud(c, SE3ICP_SOURCE, src[pi], n_src[pi], 0);
-                if (!r) r = se3icp_set_cloud(c, SE3ICP_TARGET, tgt[pi], n_tgt[pi], 0);
-            }
-            if (!r) r = se3icp_run(c, p, T_out + 16 * (size_t)pi, stats ? stats + pi : nullptr);
-            if (r) {
-                rc[ci] = r;
-                errs[ci] = se3icp_last_error();
-                break;
+    int n_threads = n_ctx < 2 ? n_ctx : 2;
+    if (const char* e = getenv("SE3ICP_BATCH_THREADS")) n_threads = std::max(1, std::min(n_ctx, atoi(e)));
+    std::vector<int> rc(n_threads, 0);
+    std::vector<std::string> errs(n_threads);
+    auto worker = [&](int t) {
+        // pair pi runs on context pi % n_ctx; thread t owns the contexts t, t + n_threads, ...
+        auto finish = [&](int pi) { return se3icp_run_finish(ctxs[pi % n_ctx], T_out + 16 * (size_t)pi, stats ? stats + pi : nullptr); };
+        int r = 0;
+        const int rounds = (n_pairs + n_ctx - 1) / n_ctx;
+        for (int round = 0; round <= rounds && !r; round++) {
+            for (int ci = t; ci < n_ctx && !r; ci += n_threads) {
+                se3icp_ctx* c = ctxs[ci];
+                const int prev = (round - 1) * n_ctx + ci, pi = round * n_ctx + ci;
+                if (round > 0 && prev < n_pairs) r = finish(prev);
+                if (r || pi >= n_pairs) continue;
+                if (device_inputs) {
+                    r = se3icp_set_cloud_device(c, SE3ICP_SOURCE, src[pi], n_src[pi]);
+                    if (!r) r = se3icp_set_cloud_device(c, SE3ICP_TARGET, tgt[pi], n_tgt[pi]);
+                } else {
+                    r = se3icp_set_cloud(c, SE3ICP_SOURCE, src[pi], n_src[pi], 0);
+                    if (!r) r = se3icp_set_cloud(c, SE3ICP_TARGET, tgt[pi], n_tgt[pi], 0);
+                }
+                if (!r) r = se3icp_run_async(c, p);
             }
         }
-        c->blocking_wait = false;
+        if (r) {
+            rc[t] = r;
+            errs[t] = se3icp_last_error();
+            for (int ci = t; ci < n_ctx; ci += n_threads)  // leave no run pending behind an error
+                if (ctxs[ci]->run_pending) se3icp_run_finish(ctxs[ci], nullptr, nullptr);
+        }
     };
-    if (n_ctx == 1) {
+    if (n_threads == 1) {
         worker(0);
     } else {
         std::vector<std::thread> th;
-        for (int ci = 0; ci < n_ctx; ci++) th.emplace_back(worker, ci);
+        for (int t = 0; t < n_threads; t++) th.emplace_back(worker, t);
         for (auto& t : th) t.join();
     }
-    for (int ci = 0; ci < n_ctx; ci++)
-        if (rc[ci]) {
-            set_last_error("%s", errs[ci].c_str());
-            return rc[ci];
+    for (int t = 0; t < n_threads; t++)
+        if (rc[t]) {
+            set_last_error("%s", errs[t].c_str());
+            return rc[t];
         }
     return SE3ICP_OK;
 }
@@ -962,7 +1019,7 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
                 SE3_TRY(launch_nn_xyz(S, T, cfg, c->dstate(), cb, st));
                 break;
             case SE3ICP_STAGE_REDUCE:
-                SE3_TRY(launch_reduce(S, T, cfg, c->dstate(), cb, c->partials.as<double>(), st));
+                SE3_TRY(launch_reduce(S, T, cfg, c->dstate(), cb, c->partials.as<double>(), SolveFusion{}, st));
                 break;
             default: {
                 FeatureArgs fa{};
@@ -1294,8 +1351,23 @@ int se3icp_trim(se3icp_ctx* c, const float* dist, size_t n, double overlap, int 
         memset(keep, 0, n);
         return SE3ICP_OK;
     }
-    SE3_TRY(launch_trim(cfg, c->dstate(), c->corr_buffers(false), (int)n, c->hist.as<unsigned int>(),
-                        c->block_eq.as<int>(), c->stream));
+    // both implementations of the rejection are reachable from here: the single-launch selection the registration loop
+    // uses on one GPU (default) and the multi-pass mask kernels of the sharded pair (SE3ICP_TRIM_MULTIPASS=1)
+    static const bool multipass = [] {
+        const char* e = getenv("SE3ICP_TRIM_MULTIPASS");
+        return e && atoi(e) != 0;
+    }();
+    SE3_TRY(c->thist.ensure((size_t)kTrimHistBins * sizeof(unsigned int)));
+    SE3_TRY(c->tcand.ensure(n * sizeof(unsigned long long)));
+    SE3_TRY(c->tcount.ensure(kTcountWords * sizeof(unsigned int)));
+    CorrBuffers cb = c->corr_buffers(false);
+    cb.thist = c->thist.as<unsigned int>();
+    cb.tcand = c->tcand.as<unsigned long long>();
+    cb.tcount = c->tcount.as<unsigned int>();
+    if (multipass)
+        SE3_TRY(launch_trim(cfg, c->dstate(), cb, (int)n, c->hist.as<unsigned int>(), c->block_eq.as<int>(), c->stream));
+    else
+        SE3_TRY(launch_trim_stage(cfg, c->dstate(), cb, (int)n, c->stream));
     SE3_CUDA(cudaMemcpyAsync(keep, c->keep.ptr, n, cudaMemcpyDeviceToHost, c->stream));
     SE3_CUDA(cudaStreamSynchronize(c->stream));
     return SE3ICP_OK;
@@ -1335,7 +1407,7 @@ int stage_reduce(se3icp_ctx* c, int variant, const double* src, const double* sr
     RunConfig cfg;
     identity_config(cfg, variant, false);
     cfg.with_cf = (conf_src && conf_tgt) ? 1 : 0;
-    SE3_TRY(launch_reduce(S, T, cfg, c->dstate(), c->corr_buffers(false), c->partials.as<double>(), c->stream));
+    SE3_TRY(launch_reduce(S, T, cfg, c->dstate(), c->corr_buffers(false), c->partials.as<double>(), SolveFusion{}, c->stream));
     if (out27) {
         std::vector<double> part((size_t)kReduceBlocks * kReducePartials);
         SE3_CUDA(cudaMemcpyAsync(part.data(), c->partials.ptr, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -25,6 +25,7 @@ struct se3icp_ctx {
     se3::DeviceBuf state;
     se3::DeviceBuf scratch;  // stage-level API staging
     se3::DeviceBuf totals, eq_total, rank_eq;  // sharded pair: all-reduced record, threshold-tie counts
+    se3::DeviceBuf thist, tcand, tcount;       // single-launch trimmed rejection: key histogram, candidates, counters / tickets
 
     // one very large pair sharded over ranks (se3icp_run_sharded)
     void* comm = nullptr;  // ncclComm_t
@@ -51,11 +52,11 @@ struct se3icp_ctx {
     se3::RunConfig cfg{};
     se3icp_params params{};
     bool run_pending = false;
-    bool blocking_wait = false;  // run_finish polls ev_end and yields instead of spinning (batches with several host threads)
     bool src_index_built = false;  // index[0].perm holds the source's Morton order of the current run
     cudaGraph_t loop_graph = nullptr;        // WHILE-loop graph of the last run (use_graph)
     cudaGraphExec_t loop_exec = nullptr;
     long long launches_per_iter = 0;
+    long long graph_instantiations = 0, graph_updates = 0;  // loop graph: executables created / re-parameterised in place
     bool graph_run = false;
     bool variant_valid = true;
     long long launches = 0;

@@ -60,8 +60,10 @@ struct IterState {
     int switch_icp;
     int done;
     int n_keep;
-    unsigned int thr_bits;
-    int eq_budget;
+    unsigned int thr_bits;  // trimmed rejection: key of the n_keep-th correspondence (float bits, complemented when keeping the largest)
+    int eq_budget;          // ... how many of the correspondences whose key equals thr_bits survive
+    int tie_limit;          // ... which: those with source index <= tie_limit (index order, like the mask kernels)
+    int pad0_;
     int repair_count;
     int hist_count;
     int switch_iter;  // value of iter when the ICP phase began (-1 before)
@@ -128,6 +130,9 @@ struct TargetView {
     double dist_scale;    // beta / tscale: stored distance uses beta * p (.cpp:465)
 };
 
+constexpr int kTcountWords = 4 + 64;
+constexpr int kTrimHistBins = 65536;  // histogram of the top 16 bits of the distance keys of one iteration
+
 struct CorrBuffers {
     double* d2_nd;   // optional [N] squared distance in the search space (12-D or 3-D), stage API
     int* idx;        // [N] matched target (original index), persists across iterations (warm start)
@@ -138,6 +143,11 @@ struct CorrBuffers {
     int* work;       // [N] queries the coherence filter could not settle this iteration
     double* ref_q;   // [12][N] query the remembered second-nearest distance belongs to (coherence filter)
     double* ref_d2nd;  // [N] exact distance to the second-nearest row at that time, < 0 = not known
+    // single-pass trimmed rejection (single-GPU runs): the kernels that store a distance also count its key in
+    // thist (non-null only then); trim_select turns the histograms into (thr_bits, tie_limit)
+    unsigned int* thist;        // [kTrimHistBins]
+    unsigned long long* tcand;  // [N] (key << 32 | source index) of the correspondences in the threshold's 16-bit bin
+    unsigned int* tcount;       // [kTcountWords]: candidate count, block tickets, coarse histogram (optimise.cu)
 };
 
 // ---- launchers (all asynchronous on `st`) ------------------------------------------------------
@@ -192,8 +202,17 @@ int launch_trim_count_eq(const RunConfig& cfg, IterState* state, const float* di
                          int* block_eq, int* eq_total, cudaStream_t st);
 int launch_trim_apply(const RunConfig& cfg, IterState* state, const float* distf, int n, const unsigned int* hist,
                       const int* block_eq, const int* rank_eq, int rank, uint8_t* keep, cudaStream_t st);
+// the tail of an iteration folded into reduce_kernel (its last block to finish runs the solve / update / stop logic)
+struct SolveFusion {
+    int enabled;
+    double* history;                 // per-iteration T_i or null
+    unsigned int* hist;              // histograms of the multi-pass trim to clear for the next iteration, or null
+    unsigned long long cond_handle;  // cudaGraphConditionalHandle of the loop graph, 0 = none
+};
 int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
-                  double* partials /*[kReduceBlocks*kReducePartials]*/, cudaStream_t st);
+                  double* partials /*[kReduceBlocks*kReducePartials]*/, const SolveFusion& fuse, cudaStream_t st);
+int launch_trim_select(const RunConfig& cfg, IterState* state, CorrBuffers cb, int begin, int end, cudaStream_t st);
+int launch_trim_stage(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, cudaStream_t st);
 int launch_sum_partials(const double* partials /*[kReduceBlocks][kReducePartials]*/, double* total /*[kReducePartials]*/,
                         cudaStream_t st);
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,

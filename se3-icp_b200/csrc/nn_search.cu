@@ -13,6 +13,7 @@
 //                       pruned traversal, FP64, warm-started from the previous correspondence.
 // Ties resolve to the smallest original index (the oracle's rule).
 #include "common.cuh"
+#include "distance_store.cuh"
 #include "internal.h"
 #include "morton.cuh"
 #include "se3_key.cuh"
@@ -71,11 +72,9 @@ __device__ __forceinline__ void write_se3_match(const TargetView& T, const RunCo
     // (target_se3_cloud_ column = beta * p even in the _with_cf variant, whose rows hold the unscaled p)
     double tx = T.rows64[9 * m + j] * T.dist_scale, ty = T.rows64[10 * m + j] * T.dist_scale,
            tz = T.rows64[11 * m + j] * T.dist_scale;
-    (void)cfg;
     double d3 = sqrt(sqdist3(q[9], q[10], q[11], tx, ty, tz));
     cb.idx[i] = T.perm12[j];
-    cb.dist[i] = d3;
-    cb.distf[i] = (float)d3;
+    store_distance(cfg, cb, i, d3);
     if (cb.d2_nd) cb.d2_nd[i] = d2_12;
 }
 
@@ -306,8 +305,7 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
             double d1sq = sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]);
             double d1 = sqrt(d1sq);
             if ((d1 + sqrt(ex * ex + ey * ey + ez * ez)) * (1.0 + 1e-12) + 1e-300 < dref) {
-                cb.dist[i] = d1;
-                cb.distf[i] = (float)d1;
+                store_distance(cfg, cb, i, d1);
                 if (cb.d2_nd) cb.d2_nd[i] = d1sq;
                 settled = true;
             }
@@ -597,8 +595,7 @@ __device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& 
     if (lane == 0) {
         double d = sqrt(tau);  // .cpp:411
         cb.idx[i] = best;
-        cb.dist[i] = d;
-        cb.distf[i] = (float)d;  // .cpp:413
+        store_distance(cfg, cb, i, d);  // .cpp:413
         if (cb.d2_nd) cb.d2_nd[i] = tau;
         if (cfg.coherence_xyz) {
             cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;

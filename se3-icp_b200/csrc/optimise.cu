@@ -1,8 +1,12 @@
 // optimise.cu — trimmed rejection, normal-equation reduction, on-device solve and loop control
 // (SURVEY §8 a9-a18).
 //
-//  * trim_*          PCL CorrespondenceRejectorTrimmed (reference .cpp:634-635,669-671): radix-select of
-//                    the n_keep-th float distance, ties at the threshold kept in index order.
+//  * trim_select     PCL CorrespondenceRejectorTrimmed (reference .cpp:634-635,669-671) in one launch: the kernels
+//                    that store a correspondence distance also count its key in a 16-bit histogram; one block turns
+//                    it into the (key, source index) pair of the n_keep-th correspondence and the reduction applies
+//                    `(key, index) <= threshold` on the fly.  Ties at the threshold are kept in index order.
+//  * trim_hist/count_eq/apply  the same selection as four all-reducible 8-bit passes + a keep mask: the sharded pair,
+//                    where the histogram has to be summed over the ranks between the passes.
 //  * reduce          one fused gather + residual/Jacobian + FP64 accumulation pass per iteration for
 //                    pt2pt (Umeyama sums, reference .cpp:692), pt2pl (.cpp:695) and GICP (.cpp:57-110,
 //                    698, with the confidence weights of .cpp:913 for run_se3_icp_with_cf).  The source
@@ -12,6 +16,7 @@
 //                    update, T accumulation, mean-distance bookkeeping and the phase / stop logic of
 //                    .cpp:709-729 (run_icp: .cpp:544-550, run_se3_pure: .cpp:1118), all on the device.
 #include "common.cuh"
+#include "distance_store.cuh"
 #include "internal.h"
 
 namespace se3 {
@@ -60,6 +65,8 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->n_keep = 0;
         st->thr_bits = 0;
         st->eq_budget = 0;
+        st->tie_limit = 0x7fffffff;
+        st->pad0_ = 0;
         st->repair_count = 0;
         st->hist_count = 0;
         st->switch_iter = -1;
@@ -80,10 +87,7 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
 // ------------------------------------------------------------------------------------------------
 // trimmed rejection
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int trim_key(float d, int keep_largest) {
-    unsigned int b = __float_as_uint(d);
-    return keep_largest ? ~b : b;
-}
+// trim_key(): distance_store.cuh
 
 // warp-cooperative: bin holding rank k in a 256-bin histogram; k becomes the rank inside that bin
 __device__ __forceinline__ int warp_select_bin(const unsigned int* __restrict__ hist, unsigned int& k, int lane) {
@@ -277,6 +281,217 @@ int launch_trim(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, u
 }
 
 // ------------------------------------------------------------------------------------------------
+// single-launch trimmed rejection (single-GPU runs)
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoarseBlocks = 64;                            // trim_bin_kernel: one block per 1024 fine bins
+constexpr int kFinePerCoarse = kTrimHistBins / kCoarseBlocks;  // 1024
+constexpr int kSelBlocks = 148;
+// CorrBuffers::tcount layout (unsigned int): [0] candidates appended, [1] ticket of trim_bin, [2] ticket of reduce,
+// [3] ticket of trim_select, [4 .. 4 + kCoarseBlocks) coarse histogram
+static_assert(kTcountWords == 4 + kCoarseBlocks, "tcount layout");
+
+// inclusive scan over the 256 threads of a block (s_warp: 8 words of shared memory)
+__device__ __forceinline__ unsigned int block_scan256(unsigned int v, unsigned int* s_warp, unsigned int& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int u = __shfl_up_sync(SE3_FULL, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    unsigned int base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned int x = s_warp[k];
+        if (k < w) base += x;
+        tot += x;
+    }
+    total = tot;
+    __syncthreads();
+    return base + incl;
+}
+
+// Step 1 of 2: which 16-bit bin of the key histogram (filled by the correspondence stage) holds rank n_keep - 1, and
+// which rank inside the bin.  64 blocks reduce 1024 bins each to one coarse count; the last block to finish walks the
+// 64 coarse counts and then the 1024 fine bins of the one that matters.  Result in IterState::thr_bits (bin) /
+// eq_budget (rank in bin); n_keep = -1 flags "fewer counted correspondences than n_keep" (keep everything).
+__global__ void __launch_bounds__(256) trim_bin_kernel(RunConfig cfg, IterState* __restrict__ state, CorrBuffers cb) {
+    if (state->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp_correspondence_end(cfg, state);
+    __shared__ unsigned int s_warp[8];
+    __shared__ int s_last;
+    __shared__ unsigned int s_coarse, s_rank;
+    const int tid = threadIdx.x;
+    const unsigned int* hist = cb.thist;
+    unsigned int* coarse = cb.tcount + 4;
+    {
+        uint4 v = reinterpret_cast<const uint4*>(hist + blockIdx.x * kFinePerCoarse)[tid];
+        unsigned int total;
+        block_scan256(v.x + v.y + v.z + v.w, s_warp, total);
+        if (tid == 0) coarse[blockIdx.x] = total;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&cb.tcount[1], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned int k0 = (unsigned int)(cfg.n_keep_target - 1);
+    {   // coarse level: 64 counts, thread t < 64 owns one
+        unsigned int cv = tid < kCoarseBlocks ? __ldcg(coarse + tid) : 0u, total;
+        unsigned int incl = block_scan256(cv, s_warp, total);
+        if (tid == 0) s_coarse = 0xffffffffu;
+        __syncthreads();
+        if (tid < kCoarseBlocks && k0 >= incl - cv && k0 < incl) {
+            s_coarse = (unsigned int)tid;
+            s_rank = k0 - (incl - cv);
+        }
+        __syncthreads();
+    }
+    if (s_coarse == 0xffffffffu) {
+        if (tid == 0) {
+            state->thr_bits = 0xffffffffu;
+            state->tie_limit = 0x7fffffff;
+            state->n_keep = -1;
+            cb.tcount[1] = 0u;
+        }
+        return;
+    }
+    {   // fine level: 1024 bins of the chosen coarse bin, 4 consecutive ones per thread
+        const unsigned int cbin = s_coarse, k1 = s_rank;
+        uint4 v = reinterpret_cast<const uint4*>(hist + cbin * kFinePerCoarse)[tid];
+        unsigned int mine = v.x + v.y + v.z + v.w, total;
+        unsigned int incl = block_scan256(mine, s_warp, total);
+        unsigned int c = incl - mine;
+        if (k1 >= c && k1 < incl) {  // exactly one thread
+            unsigned int f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (k1 >= c && k1 < c + f[e]) {
+                    state->thr_bits = cbin * kFinePerCoarse + (unsigned int)(tid * 4 + e);
+                    state->eq_budget = (int)(k1 - c);
+                    state->n_keep = cfg.n_keep_target;
+                }
+                c += f[e];
+            }
+        }
+        if (tid == 0) cb.tcount[1] = 0u;
+    }
+}
+
+// Step 2 of 2: every block appends the (key, index) pairs of its share of the correspondences that fall into the bin
+// and clears its share of the histogram for the next iteration; the last block to finish radix-selects the wanted pair,
+// 8 bits at a time from the 16 low key bits down through the index, stopping as soon as one candidate is left.  The
+// pair goes to IterState::thr_bits / tie_limit; the reduction keeps correspondence i iff (key_i, i) <= that pair.
+__global__ void __launch_bounds__(256) trim_select_kernel(RunConfig cfg, IterState* __restrict__ state, CorrBuffers cb,
+                                                           int begin, int end) {
+    if (state->done) return;
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_digit, s_rank, s_cnt;
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned int bin = state->thr_bits;
+    const unsigned int rank0 = (unsigned int)state->eq_budget;
+    const bool keep_all = state->n_keep < 0;
+    for (int b = blockIdx.x * blockDim.x + tid; b < kTrimHistBins; b += gridDim.x * blockDim.x) cb.thist[b] = 0u;
+    if (!keep_all) {
+        for (int i = begin + blockIdx.x * blockDim.x + tid; i < end; i += gridDim.x * blockDim.x) {
+            unsigned int key = trim_key(cb.distf[i], cfg.keep_largest);
+            if ((key >> 16) == bin) cb.tcand[atomicAdd(&cb.tcount[0], 1u)] = ((unsigned long long)key << 32) | (unsigned int)i;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&cb.tcount[3], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned int cnt = keep_all ? 0u : __ldcg(&cb.tcount[0]);
+    __syncthreads();  // everyone has read the state and the count before they are rewritten
+    if (tid == 0) {
+        cb.tcount[0] = 0u;
+        cb.tcount[3] = 0u;
+    }
+    if (keep_all) return;
+    unsigned long long prefix = (unsigned long long)bin << 48, mask = 0xffffull << 48;
+    unsigned int rank = rank0, remaining = cnt;
+    for (int shift = 40; shift >= 0 && remaining > 1; shift -= 8) {
+        s_hist[tid] = 0;
+        __syncthreads();
+        for (unsigned int c = tid; c < cnt; c += blockDim.x) {
+            unsigned long long v = __ldcg(&cb.tcand[c]);
+            if ((v & mask) == prefix) atomicAdd(&s_hist[(unsigned int)(v >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned int r = rank;
+            int d = warp_select_bin(s_hist, r, lane);
+            if (lane == 0) {
+                s_digit = (unsigned int)d;
+                s_rank = r;
+                s_cnt = s_hist[d];
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)s_digit << shift;
+        mask |= 0xffull << shift;
+        rank = s_rank;
+        remaining = s_cnt;
+        __syncthreads();
+    }
+    // with remaining == 1 exactly one pair matches the prefix; otherwise the prefix is the complete pair
+    for (unsigned int c = tid; c < cnt; c += blockDim.x) {
+        unsigned long long v = __ldcg(&cb.tcand[c]);
+        if ((v & mask) == prefix) {
+            state->thr_bits = (unsigned int)(v >> 32);
+            state->tie_limit = (int)(unsigned int)(v & 0xffffffffull);
+            state->eq_budget = (int)rank + 1;
+        }
+    }
+}
+
+int launch_trim_select(const RunConfig& cfg, IterState* state, CorrBuffers cb, int begin, int end, cudaStream_t st) {
+    if (!cfg.trim_active || cfg.n_keep_target <= 0) return 0;
+    static_assert(kFinePerCoarse == 256 * 4, "trim_bin_kernel: one uint4 per thread");
+    trim_bin_kernel<<<kCoarseBlocks, 256, 0, st>>>(cfg, state, cb);
+    int g = (end - begin + 1023) / 1024;
+    if (g > kSelBlocks) g = kSelBlocks;
+    if (g < 1) g = 1;
+    trim_select_kernel<<<g, 256, 0, st>>>(cfg, state, cb, begin, end);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// stage-level API only: histogram of given distances / keep mask from the selected pair
+__global__ void __launch_bounds__(256) trim_hist16_kernel(RunConfig cfg, const float* __restrict__ distf, int n,
+                                                           unsigned int* __restrict__ hist) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&hist[trim_key(distf[i], cfg.keep_largest) >> 16], 1u);
+}
+
+__global__ void __launch_bounds__(256) trim_mask_kernel(RunConfig cfg, const IterState* __restrict__ state,
+                                                         const float* __restrict__ distf, int n, uint8_t* __restrict__ keep) {
+    const unsigned int thr = state->thr_bits;
+    const int lim = state->tie_limit;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        keep[i] = trim_keeps(trim_key(distf[i], cfg.keep_largest), i, thr, lim);
+}
+
+int launch_trim_stage(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, cudaStream_t st) {
+    int g = (n + 255) / 256;
+    if (g > 148 * 4) g = 148 * 4;
+    SE3_CUDA(cudaMemsetAsync(cb.thist, 0, kTrimHistBins * sizeof(unsigned int), st));
+    SE3_CUDA(cudaMemsetAsync(cb.tcount, 0, kTcountWords * sizeof(unsigned int), st));
+    trim_hist16_kernel<<<g, 256, 0, st>>>(cfg, cb.distf, n, cb.thist);
+    SE3_TRY(launch_trim_select(cfg, state, cb, 0, n, st));
+    trim_mask_kernel<<<g, 256, 0, st>>>(cfg, state, cb.distf, n, cb.keep);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // reduction.  Partial record (kReducePartials doubles per block):
 //   pt2pl / gicp : [0..20] upper triangle of JTJ (row-major), [21..26] JTr
 //   pt2pt        : [0..2] sum(s-a), [3..5] sum(t-b), [6..14] sum (t-b)(s-a)^T row-major
@@ -284,13 +499,345 @@ int launch_trim(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, u
 // ------------------------------------------------------------------------------------------------
 constexpr int kAcc = 29;
 
+// ------------------------------------------------------------------------------------------------
+// solve + update (one warp)
+// ------------------------------------------------------------------------------------------------
+// Pivoted LDL^T of the symmetric 6x6 normal matrix (diagonal pivoting: the largest remaining |diagonal| is moved to
+// position k, like Eigen::LDLT, which Open3D's SolveLinearSystemPSD calls), then the two triangular solves; a zero
+// pivot zeroes its column instead of dividing (rank-deficient systems), a non-finite solution is reported as failure.
+// Carried out by a whole thread block on shared memory: thread 6 r + c owns entry (r, c), every
+// elimination step is a handful of parallel phases instead of a chain of dependent local-memory accesses in one
+// thread (the round-1 single-thread form cost 24 us per iteration; its loops could not be force-unrolled into
+// registers because nvcc 12.9 miscompiles that for sm_100a).  tot: 21 upper-triangular JTJ entries (row-major) + 6 JTr; solves JTJ x = -JTr.
+// Every thread of the block must call it; x / ok are valid for every thread afterwards.
+struct Ldlt6Shared {
+    double A[6][6], L[6][6], D[6], y[6], z[6], x[6];
+    int perm[6], piv, ok;
+};
+
+__device__ void ldlt6_solve_block(const double* tot, Ldlt6Shared& S) {
+    const int t = threadIdx.x, r = t / 6, c = t % 6;
+    const bool mine = t < 36;
+    if (mine) {
+        const int a = r < c ? r : c, b = r < c ? c : r;
+        S.A[r][c] = tot[a * 6 - a * (a - 1) / 2 + (b - a)];  // row-major upper triangle: row a starts at 6a - a(a-1)/2
+        S.L[r][c] = 0.0;
+    }
+    if (t < 6) S.perm[t] = t;
+    __syncthreads();
+    for (int k = 0; k < 6; k++) {
+        if (t == 0) {
+            int piv = k;
+            double big = fabs(S.A[k][k]);
+            for (int i = k + 1; i < 6; i++) {
+                double v = fabs(S.A[i][i]);
+                if (v > big) {
+                    big = v;
+                    piv = i;
+                }
+            }
+            S.piv = piv;
+        }
+        __syncthreads();
+        const int piv = S.piv;
+        if (piv != k) {  // symmetric row/column swap k <-> piv of A, row swap of L, entry swap of perm
+            const int mr = r == k ? piv : (r == piv ? k : r), mc = c == k ? piv : (c == piv ? k : c);
+            double va = 0.0, vl = 0.0;
+            int vp = 0;
+            if (mine) {
+                va = S.A[mr][mc];
+                vl = S.L[mr][c];
+            }
+            if (t < 6) vp = S.perm[t == k ? piv : (t == piv ? k : t)];
+            __syncthreads();
+            if (mine) {
+                S.A[r][c] = va;
+                S.L[r][c] = vl;
+            }
+            if (t < 6) S.perm[t] = vp;
+            __syncthreads();
+        }
+        const double d = S.A[k][k];
+        const bool nz = d != 0.0;
+        if (t < 6) {
+            if (t == k) {
+                S.D[k] = d;
+                S.L[k][k] = 1.0;
+            } else if (t > k) {
+                S.L[t][k] = nz ? S.A[t][k] / d : 0.0;
+            }
+        }
+        __syncthreads();
+        if (mine && r > k && c > k && nz) S.A[r][c] = S.A[r][c] - S.L[r][k] * d * S.L[c][k];
+        __syncthreads();
+    }
+    if (t == 0) {
+        for (int i = 0; i < 6; i++) S.y[i] = -tot[21 + S.perm[i]];  // y = P b
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < i; j++) S.y[i] -= S.L[i][j] * S.y[j];
+        for (int i = 0; i < 6; i++) S.z[i] = S.D[i] != 0.0 ? S.y[i] / S.D[i] : 0.0;
+        for (int i = 5; i >= 0; i--)
+            for (int j = i + 1; j < 6; j++) S.z[i] -= S.L[j][i] * S.z[j];
+        int ok = 1;
+        for (int i = 0; i < 6; i++) {
+            S.x[S.perm[i]] = S.z[i];
+            ok = ok && isfinite(S.z[i]);
+        }
+        S.ok = ok;
+    }
+    __syncthreads();
+}
+
+// Open3D TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x3..5 (row-major out)
+__device__ void vector6_to_T(const double x[6], double Tm[16]) {
+    double cx = cos(x[0]), sx = sin(x[0]), cy = cos(x[1]), sy = sin(x[1]), cz = cos(x[2]), sz = sin(x[2]);
+    // Rz*Ry*Rx expanded
+    Tm[0] = cz * cy;  Tm[1] = cz * sy * sx - sz * cx;  Tm[2] = cz * sy * cx + sz * sx;  Tm[3] = x[3];
+    Tm[4] = sz * cy;  Tm[5] = sz * sy * sx + cz * cx;  Tm[6] = sz * sy * cx - cz * sx;  Tm[7] = x[4];
+    Tm[8] = -sy;      Tm[9] = cy * sx;                 Tm[10] = cy * cx;                Tm[11] = x[5];
+    Tm[12] = 0.0;     Tm[13] = 0.0;                    Tm[14] = 0.0;                    Tm[15] = 1.0;
+}
+
+__device__ double det3(const double A[3][3]) {
+    return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+}
+
+// Kabsch rotation from sigma = (1/K) sum (t - mu_t)(s - mu_s)^T  (Eigen::umeyama, no scaling)
+__device__ void kabsch_rotation(const double Sg[3][3], double R[3][3]) {
+    double a6[6];
+    {   // Sg^T Sg
+        double G[3][3];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) G[i][j] = Sg[0][i] * Sg[0][j] + Sg[1][i] * Sg[1][j] + Sg[2][i] * Sg[2][j];
+        a6[0] = G[0][0], a6[1] = G[0][1], a6[2] = G[0][2], a6[3] = G[1][1], a6[4] = G[1][2], a6[5] = G[2][2];
+    }
+    double ev[3], Va[3][3];
+    eig3_sym(a6, ev, Va);
+    double V[3][3], U[3][3], sv[3];
+    for (int c = 0; c < 3; c++) {  // descending singular values
+        int src = 2 - c;
+        sv[c] = sqrt(fmax(ev[src], 0.0));
+        for (int r = 0; r < 3; r++) V[r][c] = Va[r][src];
+    }
+    double u[3][3];  // u[c] = column c
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) u[c][r] = Sg[r][0] * V[0][c] + Sg[r][1] * V[1][c] + Sg[r][2] * V[2][c];
+    auto nrm = [](const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    auto dot3 = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    auto cross3 = [](const double* a, const double* b, double* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1];
+        o[1] = a[2] * b[0] - a[0] * b[2];
+        o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    double n0 = nrm(u[0]);
+    if (n0 > 0.0) { for (int r = 0; r < 3; r++) u[0][r] /= n0; } else { u[0][0] = 1; u[0][1] = 0; u[0][2] = 0; }
+    double tiny = 1e-14 * fmax(sv[0], 1e-300);
+    double d10 = dot3(u[1], u[0]);
+    for (int r = 0; r < 3; r++) u[1][r] -= d10 * u[0][r];
+    double n1 = nrm(u[1]);
+    if (n1 > tiny) {
+        for (int r = 0; r < 3; r++) u[1][r] /= n1;
+    } else {
+        double t[3] = {fabs(u[0][0]) < 0.9 ? 1.0 : 0.0, fabs(u[0][0]) < 0.9 ? 0.0 : 1.0, 0.0};
+        cross3(u[0], t, u[1]);
+        double nn = nrm(u[1]);
+        for (int r = 0; r < 3; r++) u[1][r] /= nn;
+    }
+    double d20 = dot3(u[2], u[0]);
+    for (int r = 0; r < 3; r++) u[2][r] -= d20 * u[0][r];
+    double d21 = dot3(u[2], u[1]);
+    for (int r = 0; r < 3; r++) u[2][r] -= d21 * u[1][r];
+    double n2 = nrm(u[2]);
+    if (n2 > tiny) {
+        for (int r = 0; r < 3; r++) u[2][r] /= n2;
+    } else {
+        cross3(u[0], u[1], u[2]);
+    }
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) U[r][c] = u[c][r];
+    double d = (det3(U) * det3(V) < 0.0) ? -1.0 : 1.0;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + d * U[r][2] * V[c][2];
+}
+
+// fixed-order sum of the per-block records into one record (input of the cross-rank all-reduce)
+__global__ void __launch_bounds__(32) sum_partials_kernel(const double* __restrict__ partials, double* __restrict__ total) {
+    int lane = threadIdx.x;
+    double s = 0.0;
+    if (lane < kAcc)
+        for (int b = 0; b < kReduceBlocks; b++) s += partials[b * kReducePartials + lane];
+    total[lane] = s;
+}
+
+int launch_sum_partials(const double* partials, double* total, cudaStream_t st) {
+    sum_partials_kernel<<<1, 32, 0, st>>>(partials, total);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Executed by one whole block of 256 threads: the stand-alone kernel below (sharded pair, stage API) or the last block
+// of reduce_kernel to finish (single-GPU loop).  cond_handle != 0: the caller is the last node of the captured loop
+// body and tells the WHILE node whether to run it again.
+__device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState* __restrict__ gst,
+                                                const double* __restrict__ partials, int n_records,
+                                                double* __restrict__ history, unsigned int* __restrict__ hist,
+                                                unsigned long long cond_handle) {
+    // The bookkeeping below touches the state ~150 times from one thread; work on a shared-memory copy (one
+    // parallel load, one parallel store) instead of a chain of dependent global accesses.
+    static_assert(sizeof(IterState) % 8 == 0, "IterState is copied as 64-bit words");
+    __shared__ IterState s_state;
+    {
+        // L2 loads: when this runs as the tail of reduce_kernel, other blocks have just written parts of the state
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gst);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_state);
+        for (int k = threadIdx.x; k < (int)(sizeof(IterState) / 8); k += blockDim.x) dst[k] = __ldcg(src + k);
+    }
+    IterState* st = &s_state;
+    __shared__ double tot[kReducePartials];
+    __shared__ double wsum[8][kReducePartials];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    {   // fixed-order sum of the per-block records: warp w takes records w, w+8, ...; then the 8 warp sums in order
+        double s = 0.0;
+        if (lane < kAcc)
+            for (int b = w; b < n_records; b += 8) s += __ldcg(&partials[b * kReducePartials + lane]);
+        wsum[w][lane] = s;
+    }
+    if (hist)
+        for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) hist[k] = 0;  // ready for the next iteration's trim
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += wsum[k][threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    __shared__ Ldlt6Shared s_ldlt;
+    const bool gauss_newton = cfg.variant != SE3ICP_PT2PT && tot[28] > 0.0;  // block-uniform
+    if (gauss_newton) ldlt6_solve_block(tot, s_ldlt);
+    if (threadIdx.x == 0) {
+    const double K = tot[28];
+    const double mean = tot[27] / K;  // 0/0 -> NaN exactly as the reference
+    double Ti[16];
+    for (int k = 0; k < 16; k++) Ti[k] = (k % 5 == 0) ? 1.0 : 0.0;
+
+    if (K > 0.0) {
+        if (cfg.variant == SE3ICP_PT2PT) {
+            const double* Tm = st->T_total;
+            double c0[3] = {cfg.has_se3 ? 0.0 : st->c_src[0], cfg.has_se3 ? 0.0 : st->c_src[1],
+                            cfg.has_se3 ? 0.0 : st->c_src[2]};
+            double a[3], b[3] = {0, 0, 0};
+            for (int r = 0; r < 3; r++) a[r] = Tm[4 * r] * c0[0] + Tm[4 * r + 1] * c0[1] + Tm[4 * r + 2] * c0[2] + Tm[4 * r + 3];
+            if (!cfg.has_se3)
+                for (int r = 0; r < 3; r++) b[r] = st->c_tgt[r];
+            double ms[3] = {tot[0] / K, tot[1] / K, tot[2] / K};  // mu_s - a
+            double mt[3] = {tot[3] / K, tot[4] / K, tot[5] / K};  // mu_t - b
+            double Sg[3][3];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) Sg[r][c] = tot[6 + 3 * r + c] / K - mt[r] * ms[c];
+            double R[3][3];
+            kabsch_rotation(Sg, R);
+            double mus[3] = {ms[0] + a[0], ms[1] + a[1], ms[2] + a[2]};
+            double mut[3] = {mt[0] + b[0], mt[1] + b[1], mt[2] + b[2]};
+            for (int r = 0; r < 3; r++) {
+                for (int c = 0; c < 3; c++) Ti[4 * r + c] = R[r][c];
+                Ti[4 * r + 3] = mut[r] - (R[r][0] * mus[0] + R[r][1] * mus[1] + R[r][2] * mus[2]);
+            }
+        } else {
+            if (s_ldlt.ok) vector6_to_T(s_ldlt.x, Ti);
+        }
+    }
+
+    // bookkeeping: reference .cpp:684-686, 709-711
+    st->mse_prev = st->mse_cur;
+    st->mse_cur = mean;
+    st->mse_rel = fabs(st->mse_cur - st->mse_prev);
+    double Tn[16];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            double s = 0.0;
+            for (int k = 0; k < 4; k++) s += Ti[4 * r + k] * st->T_total[4 * k + c];
+            Tn[4 * r + c] = s;
+        }
+    double ch = 0.0;
+    for (int k = 0; k < 16; k++) {
+        double df = st->T_total[k] - Tn[k];
+        ch += df * df;
+        st->T_prev[k] = st->T_total[k];
+        st->T_i[k] = Ti[k];
+    }
+    for (int k = 0; k < 16; k++) st->T_total[k] = Tn[k];
+    st->T_change = sqrt(ch);
+    if (cfg.record_history && history && st->hist_count < cfg.max_history) {
+        for (int k = 0; k < 16; k++) history[16 * (size_t)st->hist_count + k] = Ti[k];
+        st->hist_count++;
+    }
+
+    const bool se3_now = se3_phase_active_o(cfg, st);
+    st->iter += 1;
+    if (se3_now) st->se3_iters += 1;
+    const double s = st->scale;
+    if (!cfg.has_se3) {  // run_icp .cpp:547-550
+        if (st->iter == cfg.max_iter || st->mse_rel < cfg.mse) st->done = 1;
+    } else if (cfg.pure) {  // run_se3_pure .cpp:1118
+        if (st->iter == cfg.max_se3_iter || st->mse_rel < s * cfg.mse) st->done = 1;
+    } else if (!st->switch_icp) {  // .cpp:718-723
+        if (st->iter == cfg.max_se3_iter || st->T_change < cfg.mse_switch) {
+            st->switch_icp = 1;
+            st->switch_iter = st->iter;
+            st->t_switch = global_timer_ns();
+        }
+    } else {  // .cpp:724-729
+        if (st->iter == cfg.max_iter || st->mse_rel < s * cfg.mse) st->done = 1;
+    }
+    if (st->iter >= 1000000) st->done = 1;  // hard cap (the reference would spin forever on such parameters)
+    st->total_repairs += st->repair_count;
+    st->repair_count = 0;
+    st->searched_total += (unsigned long long)st->work_count;
+    st->work_count = 0;
+    st->corr_stamped = 0;
+    st->t_mark = global_timer_ns();
+    if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, st->done ? 0u : 1u);
+    }  // thread 0
+    __syncthreads();
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_state);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(gst);
+        for (int k = threadIdx.x; k < (int)(sizeof(IterState) / 8); k += blockDim.x) dst[k] = src[k];
+    }
+}
+
+__global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterState* __restrict__ gst,
+                                                            const double* __restrict__ partials, int n_records,
+                                                            double* __restrict__ history, unsigned int* __restrict__ hist,
+                                                            unsigned long long cond_handle) {
+    if (gst->done) {
+        if (cond_handle && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
+        return;
+    }
+    solve_update_block(cfg, gst, partials, n_records, history, hist, cond_handle);
+}
+
+// fuse.enabled: the block that finishes last also sums the per-block records (fixed order, so the result does not depend
+// on which block that is), solves, updates the estimate and decides whether the loop goes on — an iteration then ends
+// with this kernel.
 __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T, RunConfig cfg, IterState* __restrict__ state,
-                                                      CorrBuffers cb, double* __restrict__ partials) {
-    if (state->done) return;
+                                                      CorrBuffers cb, double* __restrict__ partials, SolveFusion fuse) {
+    if (state->done) {
+        if (fuse.enabled && fuse.cond_handle && blockIdx.x == 0 && threadIdx.x == 0)
+            cudaGraphSetConditional((cudaGraphConditionalHandle)fuse.cond_handle, 0u);
+        return;
+    }
     __shared__ double Tm[16];
     __shared__ double sm[8][kAcc];
+    __shared__ int s_last;
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     if (blockIdx.x == 0 && threadIdx.x == 0) stamp_correspondence_end(cfg, state);
+    // trimmed rejection: either the (key, index) threshold of trim_select_kernel or the mask of the multi-pass kernels
+    const bool trim_thr = cfg.trim_active && cb.thist != nullptr;
+    const unsigned int thr_bits = trim_thr ? state->thr_bits : 0u;
+    const int tie_limit = trim_thr ? state->tie_limit : 0;
     __syncthreads();
     double acc[kAcc];
 #pragma unroll
@@ -313,7 +860,10 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
     }
 
     for (int i = S.begin + blockIdx.x * blockDim.x + threadIdx.x; i < S.end; i += gridDim.x * blockDim.x) {
-        if (cfg.trim_active && !cb.keep[i]) continue;
+        if (cfg.trim_active) {
+            if (cfg.n_keep_target <= 0) continue;
+            if (trim_thr ? !trim_keeps(trim_key(cb.distf[i], cfg.keep_largest), i, thr_bits, tie_limit) : !cb.keep[i]) continue;
+        }
         const int j = cb.idx[i];
         if (j < 0) continue;
         const double px = S.x[i], py = S.y[i], pz = S.z[i];
@@ -412,318 +962,23 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
         for (int k = 0; k < 8; k++) s += sm[k][threadIdx.x];
         partials[blockIdx.x * kReducePartials + threadIdx.x] = s;
     }
+    if (!fuse.enabled) return;
+    // last block to arrive finishes the iteration
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&cb.tcount[2], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) cb.tcount[2] = 0u;  // ready for the next launch
+    solve_update_block(cfg, state, partials, (int)gridDim.x, fuse.history, fuse.hist, fuse.cond_handle);
 }
 
 int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
-                  double* partials, cudaStream_t st) {
-    reduce_kernel<<<kReduceBlocks, 256, 0, st>>>(S, T, cfg, state, cb, partials);
+                  double* partials, const SolveFusion& fuse, cudaStream_t st) {
+    reduce_kernel<<<kReduceBlocks, 256, 0, st>>>(S, T, cfg, state, cb, partials, fuse);
     SE3_CUDA(cudaGetLastError());
     return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// solve + update (one warp)
-// ------------------------------------------------------------------------------------------------
-// pivoted LDL^T of a symmetric 6x6 (diagonal pivoting, like Eigen::LDLT which Open3D's
-// SolveLinearSystemPSD calls); returns false when the solution is not finite.  The pivot swaps are
-// predicated selects over loop indices so the compiler can unroll and keep the factorisation in registers.
-// NOTE: do not add `#pragma unroll` here — nvcc 12.9 miscompiles this function for sm_100a when the loops
-// are force-unrolled (verified against the host build of the same source; plain -O3 is correct).
-__device__ bool ldlt6_solve(const double Ain[6][6], const double bin[6], double x[6]) {
-    double A[6][6], L[6][6], D[6], b[6];
-    int perm[6];
-    for (int i = 0; i < 6; i++) {
-        perm[i] = i;
-        b[i] = bin[i];
-        for (int j = 0; j < 6; j++) {
-            A[i][j] = Ain[i][j];
-            L[i][j] = 0.0;
-        }
-    }
-    for (int k = 0; k < 6; k++) {
-        int piv = k;
-        double big = fabs(A[k][k]);
-        for (int i = k + 1; i < 6; i++) {
-            double v = fabs(A[i][i]);
-            if (v > big) {
-                big = v;
-                piv = i;
-            }
-        }
-        for (int i = k + 1; i < 6; i++) {
-            const bool sw = piv == i;  // at most one i matches
-            for (int j = 0; j < 6; j++) {  // rows k <-> i
-                double t = A[k][j], u = A[i][j];
-                A[k][j] = sw ? u : t;
-                A[i][j] = sw ? t : u;
-            }
-            for (int r = 0; r < 6; r++) {  // columns k <-> i
-                double t = A[r][k], u = A[r][i];
-                A[r][k] = sw ? u : t;
-                A[r][i] = sw ? t : u;
-            }
-            for (int j = 0; j < k; j++) {
-                double t = L[k][j], u = L[i][j];
-                L[k][j] = sw ? u : t;
-                L[i][j] = sw ? t : u;
-            }
-            int tp = perm[k], up = perm[i];
-            perm[k] = sw ? up : tp;
-            perm[i] = sw ? tp : up;
-        }
-        D[k] = A[k][k];
-        L[k][k] = 1.0;
-        const bool nz = D[k] != 0.0;
-        for (int i = k + 1; i < 6; i++) L[i][k] = nz ? A[i][k] / D[k] : 0.0;
-        for (int i = k + 1; i < 6; i++)
-            for (int j = k + 1; j < 6; j++) A[i][j] = nz ? A[i][j] - L[i][k] * D[k] * L[j][k] : A[i][j];
-    }
-    double y[6], z[6];
-    for (int i = 0; i < 6; i++) {  // y = P b (perm is data dependent: select)
-        double v = 0.0;
-        for (int j = 0; j < 6; j++) v = perm[i] == j ? b[j] : v;
-        y[i] = v;
-    }
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < i; j++) y[i] -= L[i][j] * y[j];
-    for (int i = 0; i < 6; i++) z[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
-    for (int i = 5; i >= 0; i--)
-        for (int j = i + 1; j < 6; j++) z[i] -= L[j][i] * z[j];
-    bool ok = true;
-    for (int j = 0; j < 6; j++) x[j] = 0.0;
-    for (int i = 0; i < 6; i++) {
-        for (int j = 0; j < 6; j++) x[j] = perm[i] == j ? z[i] : x[j];
-        ok = ok && isfinite(z[i]);
-    }
-    return ok;
-}
-
-// Open3D TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x3..5 (row-major out)
-__device__ void vector6_to_T(const double x[6], double Tm[16]) {
-    double cx = cos(x[0]), sx = sin(x[0]), cy = cos(x[1]), sy = sin(x[1]), cz = cos(x[2]), sz = sin(x[2]);
-    // Rz*Ry*Rx expanded
-    Tm[0] = cz * cy;  Tm[1] = cz * sy * sx - sz * cx;  Tm[2] = cz * sy * cx + sz * sx;  Tm[3] = x[3];
-    Tm[4] = sz * cy;  Tm[5] = sz * sy * sx + cz * cx;  Tm[6] = sz * sy * cx - cz * sx;  Tm[7] = x[4];
-    Tm[8] = -sy;      Tm[9] = cy * sx;                 Tm[10] = cy * cx;                Tm[11] = x[5];
-    Tm[12] = 0.0;     Tm[13] = 0.0;                    Tm[14] = 0.0;                    Tm[15] = 1.0;
-}
-
-__device__ double det3(const double A[3][3]) {
-    return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
-           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
-}
-
-// Kabsch rotation from sigma = (1/K) sum (t - mu_t)(s - mu_s)^T  (Eigen::umeyama, no scaling)
-__device__ void kabsch_rotation(const double Sg[3][3], double R[3][3]) {
-    double a6[6];
-    {   // Sg^T Sg
-        double G[3][3];
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) G[i][j] = Sg[0][i] * Sg[0][j] + Sg[1][i] * Sg[1][j] + Sg[2][i] * Sg[2][j];
-        a6[0] = G[0][0], a6[1] = G[0][1], a6[2] = G[0][2], a6[3] = G[1][1], a6[4] = G[1][2], a6[5] = G[2][2];
-    }
-    double ev[3], Va[3][3];
-    eig3_sym(a6, ev, Va);
-    double V[3][3], U[3][3], sv[3];
-    for (int c = 0; c < 3; c++) {  // descending singular values
-        int src = 2 - c;
-        sv[c] = sqrt(fmax(ev[src], 0.0));
-        for (int r = 0; r < 3; r++) V[r][c] = Va[r][src];
-    }
-    double u[3][3];  // u[c] = column c
-    for (int c = 0; c < 3; c++)
-        for (int r = 0; r < 3; r++) u[c][r] = Sg[r][0] * V[0][c] + Sg[r][1] * V[1][c] + Sg[r][2] * V[2][c];
-    auto nrm = [](const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
-    auto dot3 = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
-    auto cross3 = [](const double* a, const double* b, double* o) {
-        o[0] = a[1] * b[2] - a[2] * b[1];
-        o[1] = a[2] * b[0] - a[0] * b[2];
-        o[2] = a[0] * b[1] - a[1] * b[0];
-    };
-    double n0 = nrm(u[0]);
-    if (n0 > 0.0) { for (int r = 0; r < 3; r++) u[0][r] /= n0; } else { u[0][0] = 1; u[0][1] = 0; u[0][2] = 0; }
-    double tiny = 1e-14 * fmax(sv[0], 1e-300);
-    double d10 = dot3(u[1], u[0]);
-    for (int r = 0; r < 3; r++) u[1][r] -= d10 * u[0][r];
-    double n1 = nrm(u[1]);
-    if (n1 > tiny) {
-        for (int r = 0; r < 3; r++) u[1][r] /= n1;
-    } else {
-        double t[3] = {fabs(u[0][0]) < 0.9 ? 1.0 : 0.0, fabs(u[0][0]) < 0.9 ? 0.0 : 1.0, 0.0};
-        cross3(u[0], t, u[1]);
-        double nn = nrm(u[1]);
-        for (int r = 0; r < 3; r++) u[1][r] /= nn;
-    }
-    double d20 = dot3(u[2], u[0]);
-    for (int r = 0; r < 3; r++) u[2][r] -= d20 * u[0][r];
-    double d21 = dot3(u[2], u[1]);
-    for (int r = 0; r < 3; r++) u[2][r] -= d21 * u[1][r];
-    double n2 = nrm(u[2]);
-    if (n2 > tiny) {
-        for (int r = 0; r < 3; r++) u[2][r] /= n2;
-    } else {
-        cross3(u[0], u[1], u[2]);
-    }
-    for (int c = 0; c < 3; c++)
-        for (int r = 0; r < 3; r++) U[r][c] = u[c][r];
-    double d = (det3(U) * det3(V) < 0.0) ? -1.0 : 1.0;
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + d * U[r][2] * V[c][2];
-}
-
-// fixed-order sum of the per-block records into one record (input of the cross-rank all-reduce)
-__global__ void __launch_bounds__(32) sum_partials_kernel(const double* __restrict__ partials, double* __restrict__ total) {
-    int lane = threadIdx.x;
-    double s = 0.0;
-    if (lane < kAcc)
-        for (int b = 0; b < kReduceBlocks; b++) s += partials[b * kReducePartials + lane];
-    total[lane] = s;
-}
-
-int launch_sum_partials(const double* partials, double* total, cudaStream_t st) {
-    sum_partials_kernel<<<1, 32, 0, st>>>(partials, total);
-    SE3_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// cond_handle != 0: this kernel is the last node of the captured loop body and tells the WHILE node whether
-// to run it again
-__global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterState* __restrict__ gst,
-                                                            const double* __restrict__ partials, int n_records,
-                                                            double* __restrict__ history, unsigned int* __restrict__ hist,
-                                                            unsigned long long cond_handle) {
-    if (gst->done) {
-        if (cond_handle && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
-        return;
-    }
-    // The bookkeeping below touches the state ~150 times from one thread; work on a shared-memory copy (one
-    // parallel load, one parallel store) instead of a chain of dependent global accesses.
-    static_assert(sizeof(IterState) % 8 == 0, "IterState is copied as 64-bit words");
-    __shared__ IterState s_state;
-    {
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gst);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_state);
-        for (int k = threadIdx.x; k < (int)(sizeof(IterState) / 8); k += blockDim.x) dst[k] = src[k];
-    }
-    IterState* st = &s_state;
-    __shared__ double tot[kReducePartials];
-    __shared__ double wsum[8][kReducePartials];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    {   // fixed-order sum of the per-block records: warp w takes records w, w+8, ...; then the 8 warp sums in order
-        double s = 0.0;
-        if (lane < kAcc)
-            for (int b = w; b < n_records; b += 8) s += partials[b * kReducePartials + lane];
-        wsum[w][lane] = s;
-    }
-    if (hist)
-        for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) hist[k] = 0;  // ready for the next iteration's trim
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += wsum[k][threadIdx.x];
-        tot[threadIdx.x] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-    const double K = tot[28];
-    const double mean = tot[27] / K;  // 0/0 -> NaN exactly as the reference
-    double Ti[16];
-    for (int k = 0; k < 16; k++) Ti[k] = (k % 5 == 0) ? 1.0 : 0.0;
-
-    if (K > 0.0) {
-        if (cfg.variant == SE3ICP_PT2PT) {
-            const double* Tm = st->T_total;
-            double c0[3] = {cfg.has_se3 ? 0.0 : st->c_src[0], cfg.has_se3 ? 0.0 : st->c_src[1],
-                            cfg.has_se3 ? 0.0 : st->c_src[2]};
-            double a[3], b[3] = {0, 0, 0};
-            for (int r = 0; r < 3; r++) a[r] = Tm[4 * r] * c0[0] + Tm[4 * r + 1] * c0[1] + Tm[4 * r + 2] * c0[2] + Tm[4 * r + 3];
-            if (!cfg.has_se3)
-                for (int r = 0; r < 3; r++) b[r] = st->c_tgt[r];
-            double ms[3] = {tot[0] / K, tot[1] / K, tot[2] / K};  // mu_s - a
-            double mt[3] = {tot[3] / K, tot[4] / K, tot[5] / K};  // mu_t - b
-            double Sg[3][3];
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) Sg[r][c] = tot[6 + 3 * r + c] / K - mt[r] * ms[c];
-            double R[3][3];
-            kabsch_rotation(Sg, R);
-            double mus[3] = {ms[0] + a[0], ms[1] + a[1], ms[2] + a[2]};
-            double mut[3] = {mt[0] + b[0], mt[1] + b[1], mt[2] + b[2]};
-            for (int r = 0; r < 3; r++) {
-                for (int c = 0; c < 3; c++) Ti[4 * r + c] = R[r][c];
-                Ti[4 * r + 3] = mut[r] - (R[r][0] * mus[0] + R[r][1] * mus[1] + R[r][2] * mus[2]);
-            }
-        } else {
-            double A[6][6], rhs[6], x[6];
-            int o = 0;
-            for (int a = 0; a < 6; a++)
-                for (int b = a; b < 6; b++) {
-                    A[a][b] = tot[o];
-                    A[b][a] = tot[o];
-                    o++;
-                }
-            for (int a = 0; a < 6; a++) rhs[a] = -tot[21 + a];
-            if (ldlt6_solve(A, rhs, x)) vector6_to_T(x, Ti);
-        }
-    }
-
-    // bookkeeping: reference .cpp:684-686, 709-711
-    st->mse_prev = st->mse_cur;
-    st->mse_cur = mean;
-    st->mse_rel = fabs(st->mse_cur - st->mse_prev);
-    double Tn[16];
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) {
-            double s = 0.0;
-            for (int k = 0; k < 4; k++) s += Ti[4 * r + k] * st->T_total[4 * k + c];
-            Tn[4 * r + c] = s;
-        }
-    double ch = 0.0;
-    for (int k = 0; k < 16; k++) {
-        double df = st->T_total[k] - Tn[k];
-        ch += df * df;
-        st->T_prev[k] = st->T_total[k];
-        st->T_i[k] = Ti[k];
-    }
-    for (int k = 0; k < 16; k++) st->T_total[k] = Tn[k];
-    st->T_change = sqrt(ch);
-    if (cfg.record_history && history && st->hist_count < cfg.max_history) {
-        for (int k = 0; k < 16; k++) history[16 * (size_t)st->hist_count + k] = Ti[k];
-        st->hist_count++;
-    }
-
-    const bool se3_now = se3_phase_active_o(cfg, st);
-    st->iter += 1;
-    if (se3_now) st->se3_iters += 1;
-    const double s = st->scale;
-    if (!cfg.has_se3) {  // run_icp .cpp:547-550
-        if (st->iter == cfg.max_iter || st->mse_rel < cfg.mse) st->done = 1;
-    } else if (cfg.pure) {  // run_se3_pure .cpp:1118
-        if (st->iter == cfg.max_se3_iter || st->mse_rel < s * cfg.mse) st->done = 1;
-    } else if (!st->switch_icp) {  // .cpp:718-723
-        if (st->iter == cfg.max_se3_iter || st->T_change < cfg.mse_switch) {
-            st->switch_icp = 1;
-            st->switch_iter = st->iter;
-            st->t_switch = global_timer_ns();
-        }
-    } else {  // .cpp:724-729
-        if (st->iter == cfg.max_iter || st->mse_rel < s * cfg.mse) st->done = 1;
-    }
-    if (st->iter >= 1000000) st->done = 1;  // hard cap (the reference would spin forever on such parameters)
-    st->total_repairs += st->repair_count;
-    st->repair_count = 0;
-    st->searched_total += (unsigned long long)st->work_count;
-    st->work_count = 0;
-    st->corr_stamped = 0;
-    st->t_mark = global_timer_ns();
-    if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, st->done ? 0u : 1u);
-    }  // thread 0
-    __syncthreads();
-    {
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_state);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(gst);
-        for (int k = threadIdx.x; k < (int)(sizeof(IterState) / 8); k += blockDim.x) dst[k] = src[k];
-    }
 }
 
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,

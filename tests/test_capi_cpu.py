@@ -22,7 +22,7 @@ def test_header_symbols_exported(capi):
     for n in names:
         assert hasattr(lib, n), "libse3icp_cuda.so does not export %s" % n
     assert sorted(capi.EXPORTED_SYMBOLS) == names
-    assert lib.se3icp_abi_version() == 2
+    assert lib.se3icp_abi_version() == 3
 
 
 def test_default_params_match_reference_ctor(capi):

@@ -505,6 +505,34 @@ def test_graph_loop_equals_host_loop(ctx, capi, bunny4k, entry_name, variant, ov
     assert sb.kernel_launches > 0
 
 
+def test_loop_graph_is_kept_and_updated_in_place(capi, c1, bunny4k):
+    """The context instantiates its loop graph once and re-parameterises it for later pairs (other sizes, other
+    buffers, other parameters); only another launch sequence (trimming on/off) may build a new executable.  Results
+    must equal those of a fresh context."""
+    problems = [c1, bunny4k, (W.bunny_problem("easy", seed=5, n_points=9000)), c1]
+    fresh = []
+    for src, tgt, _ in problems:
+        with capi.Context(0) as f:
+            f.set_cloud(capi.SOURCE, src)
+            f.set_cloud(capi.TARGET, tgt)
+            fresh.append(f.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM)))
+    with capi.Context(0) as c:
+        for (src, tgt, _), (Tf, sf) in zip(problems, fresh):
+            c.set_cloud(capi.SOURCE, src)
+            c.set_cloud(capi.TARGET, tgt)
+            T, s = c.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM))
+            np.testing.assert_array_equal(T, Tf)
+            assert (s.num_iterations, s.num_pure_se3_iterations) == (sf.num_iterations, sf.num_pure_se3_iterations)
+            assert s.graph_instantiations == 1
+        # another variant and entry: same launch sequence, still the same executable
+        T, s = c.run(capi.default_params(variant="gicp", entry=capi.RUN_ICP, **RRM))
+        assert s.graph_instantiations == 1
+        # trimming adds the two selection kernels to the iteration: a new executable, once
+        for _ in range(2):
+            T, s = c.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **dict(RRM, estimated_overlap=0.8)))
+            assert s.graph_instantiations == 2
+
+
 @pytest.mark.parametrize("problem", ["c1", "bunny", "kitti"])
 def test_coherence_filter_is_exact(ctx, capi, c1, bunny4k, problem):
     """nn_coherence=1 (skip queries whose remembered match is provably still nearest) must not change a bit"""
