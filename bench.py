@@ -17,7 +17,15 @@ independent pairs (32 -> 256 pairs at 8 GPUs, the named configuration); no data-
   cpu_baseline  the CPU oracle (a port) timed on the host cores over the 8 unique pairs of the same workload, N = 1
             only; the reference's own source, compiled against stand-in Open3D/PCL/Eigen (oracle/_ref), is 3-4x slower
             than the port and is reported next to it, not as the baseline
+  configs   (N = 1) every other single-GPU configuration of BASELINE.json through the same C ABI — configs[0] fixture,
+            configs[1] bunny x 3 difficulty levels x 3 variants, configs[3] lounge-like with_cf — each with its device
+            time and its parity against the CPU oracle on the same input (rotation / translation difference, iteration
+            counts).  Parity lines, not bench values.
+  sharded_pair  (N > 1) BASELINE.json configs[4]: ONE ~10 M-point pair, se3_pt2pl, through se3icp_run_sharded with the
+            library's own NCCL communicator (target replicated, source queries split over the N ranks, one 29-double
+            all-reduce per iteration); device time max over ranks, next to the same pair on rank 0's GPU alone.
   --impl reference   times only that CPU path (rank 0), same metric/config
+  At N > 1 the driver's vs_reference ratio divides N GPUs by ONE host process; it is not a per-GPU speed-up.
 """
 import argparse
 import json
@@ -37,7 +45,19 @@ import workloads as W  # noqa: E402
 METRIC = "SE(3)-ICP registrations/s @KITTI-size clouds (se3_gicp)"
 UNIT = "registrations/s"
 UNIQUE_PAIRS = 8  # distinct synthetic scenes per GPU, cycled to pairs_per_gpu
-NCU_TRAFFIC_BYTES = 33188096  # see roofline.traffic below (31 603 456 read + 1 584 640 written)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # written from the committed ncu capture
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json names the report and the launch).  A profiler number, not measured in this run."""
+    try:
+        with open(NCU_TRAFFIC_FILE) as f:
+            t = json.load(f)
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"]), "ncu capture %s (%s); not measured in this run" % (
+            t["report"], t["launch"])
+    except Exception:
+        return None, "no committed ncu capture found"
 
 
 def parse():
@@ -197,6 +217,111 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+RRM_PARAMS = dict(estimated_overlap=1.0, max_num_se3_iterations=10, mse=1e-5, mse_switch_error=5e-5,
+                  number_of_nn_for_LRF=90)  # run_registration_method.cpp:38-42 = benchmark_synthetic.cpp:356-360
+
+
+def configs_block(capi, orc, device):
+    """Every single-GPU configuration of BASELINE.json other than the headline one, GPU vs CPU oracle on the same input."""
+    cases = [("configs[0] fixture se3_pt2pl", W.load_c1(), "RUN_SE3_ICP", "pt2pl", RRM_PARAMS)]
+    for level, seed in (("easy", 1), ("moderate", 2), ("difficult", 3)):
+        prob = W.bunny_problem(level, seed=seed)
+        for v in ("pt2pt", "pt2pl", "gicp"):
+            cases.append(("configs[1] bunny %s se3_%s" % (level, v), prob, "RUN_SE3_ICP", v, RRM_PARAMS))
+    cases.append(("configs[3] lounge-like se3_gicp_with_cf", W.rgbd_pair(seed=0), "RUN_SE3_ICP_CF", "gicp", W.LOUNGE_PARAMS))
+    out = []
+    with capi.Context(device) as ctx:
+        for name, (src, tgt, T_gt), entry, variant, kw in cases:
+            ctx.set_cloud(capi.SOURCE, src)
+            ctx.set_cloud(capi.TARGET, tgt)
+            pg = capi.default_params(variant=variant, entry=getattr(capi, entry), reuse_features=0, **kw)
+            runs = [ctx.run(pg) for _ in range(4)][1:]  # first run warms the buffers
+            T, st = runs[-1]
+            t0 = time.perf_counter()
+            To, so, _ = orc.run(src, tgt, orc.default_params(variant=variant, entry=getattr(orc, entry), **kw))
+            cpu_ms = 1e3 * (time.perf_counter() - t0)
+            extent = float(np.ptp(tgt, axis=0).max())
+            out.append({"config": name, "points": [len(src), len(tgt)],
+                        "gpu_ms": float(np.median([s.time_total_ms for _, s in runs])), "setup_ms": float(st.time_setup_ms),
+                        "iterations": [int(st.num_iterations), int(st.num_pure_se3_iterations)],
+                        "oracle_iterations": [int(so.num_iterations), int(so.num_pure_se3_iterations)],
+                        "iterations_equal": bool(st.num_iterations == so.num_iterations and
+                                                 st.num_pure_se3_iterations == so.num_pure_se3_iterations),
+                        "rot_vs_oracle_rad": W.rotation_error(T, To),
+                        "transl_vs_oracle_rel_extent": float(np.abs(T[:3, 3] - To[:3, 3]).max() / extent),
+                        "rot_vs_gt_rad": W.rotation_error(T, T_gt), "oracle_cpu_ms": cpu_ms})
+    return out
+
+
+def sharded_pair_block(capi, sharding, torch, dist, local_rank, rank, world):
+    """BASELINE.json configs[4]: one ~10 M-point pair, se3_pt2pl, source queries sharded over the ranks."""
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        src, tgt, _ = W.rgbd_pair_device(seed=0, device=dev)
+        # deal the source out in blocks so that every rank's contiguous range samples the whole image (sharding.dealt_order)
+        src = src[torch.from_numpy(sharding.dealt_order(src.shape[0], world)).to(dev)].contiguous()
+        sizes = torch.tensor([src.shape[0], tgt.shape[0]], dtype=torch.int64, device=dev)
+    else:
+        sizes = torch.zeros(2, dtype=torch.int64, device=dev)
+    dist.broadcast(sizes, src=0)
+    n_src, n_tgt = int(sizes[0]), int(sizes[1])
+    if rank != 0:
+        src = torch.empty((n_src, 3), dtype=torch.float64, device=dev)
+        tgt = torch.empty((n_tgt, 3), dtype=torch.float64, device=dev)
+    dist.broadcast(src, src=0)  # every rank holds both clouds (target replicated, source needed for its neighbourhoods)
+    dist.broadcast(tgt, src=0)
+    torch.cuda.synchronize()
+    p = capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, reuse_features=0, **RRM_PARAMS)
+    res = None
+    with capi.Context(local_rank) as ctx:
+        sharding.init_sharded_comm(ctx, capi, dist, dev)  # the library's own NCCL communicator (se3icp_comm_init)
+        comm_rank, comm_size = ctx.comm_info()
+        ctx.set_cloud_device(capi.SOURCE, src.data_ptr(), n_src)
+        ctx.set_cloud_device(capi.TARGET, tgt.data_ptr(), n_tgt)
+        b, e = sharding.shard_range(n_src, world, rank)
+        runs = []
+        for _ in range(3):  # the first run allocates
+            dist.barrier()
+            runs.append(ctx.run_sharded(p, b, e))
+        Ts, ss = runs[-1]
+        ms_n = sharding.max_over_ranks(min(r[1].time_total_ms for r in runs[1:]), dist, dev)
+        setup_n = sharding.max_over_ranks(ss.time_setup_ms, dist, dev)
+        per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+        per_rank[rank] = ss.time_se3_correspondence_search_ms  # device time this rank spent searching (both phases)
+        dist.all_reduce(per_rank)
+        identical = torch.tensor(Ts.reshape(-1), dtype=torch.float64, device=dev)
+        lo, hi = identical.clone(), identical.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same_on_all_ranks = bool(torch.equal(lo, hi))
+        dist.barrier()
+        if rank == 0:  # the same pair on one GPU, the other ranks idle
+            one = [ctx.run(p) for _ in range(2)]
+            T1, s1 = one[-1]
+            res = {"config": "configs[4]: one pair, se3_pt2pl, overlap 1.0, target replicated, source queries sharded, "
+                             "29-double all-reduce per iteration", "points": [n_src, n_tgt], "n_gpus": world,
+                   "library_comm": {"rank": comm_rank, "n_ranks": comm_size, "owner": "se3icp_comm_init (NCCL)"},
+                   "ms_1gpu": float(s1.time_total_ms), "setup_ms_1gpu": float(s1.time_setup_ms),
+                   "ms_Ngpu": float(ms_n), "setup_ms_Ngpu": float(setup_n), "speedup": float(s1.time_total_ms / ms_n),
+                   "iterations": [int(ss.num_iterations), int(ss.num_pure_se3_iterations)],
+                   "iterations_1gpu": [int(s1.num_iterations), int(s1.num_pure_se3_iterations)],
+                   "rot_vs_1gpu_rad": W.rotation_error(Ts, T1),
+                   "transl_vs_1gpu": float(np.linalg.norm(Ts[:3, 3] - T1[:3, 3])),
+                   "identical_on_all_ranks": same_on_all_ranks, "loop": ss_loop_name(ss),
+                   "search_ms_per_rank": [round(float(x), 2) for x in per_rank.cpu()],
+                   "source_order": "dealt to the ranks in blocks of 4096 points (sharding.dealt_order)",
+                   "timing": "library CUDA events around set-up + loop, max over ranks, best of 2 after a warm-up run"}
+        dist.barrier()
+    del src, tgt
+    torch.cuda.empty_cache()
+    return res
+
+
+def ss_loop_name(stats):
+    return "one CUDA graph (conditional WHILE node)" if stats.graph_instantiations > 0 else "host-driven, one sync per iteration"
+
+
+# --------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -312,8 +437,8 @@ def run_b200(args):
         c0.set_cloud_device(capi.SOURCE, dev[0][0].data_ptr(), len(s0))
         c0.set_cloud_device(capi.TARGET, dev[0][1].data_ptr(), len(t0))
         _, st0 = c0.run(params)
-        stage_ms = {"nn_se3_full_search_all_queries": c0.time_stage(capi.STAGE_NN_SE3, 10),
-                    "nn_xyz_full_search_all_queries": c0.time_stage(capi.STAGE_NN_XYZ, 10),
+        stage_ms = {"nn_se3_cold_search_all_queries": c0.time_stage(capi.STAGE_NN_SE3, 10),
+                    "nn_xyz_cold_search_all_queries": c0.time_stage(capi.STAGE_NN_XYZ, 10),
                     "reduce_gicp": c0.time_stage(capi.STAGE_REDUCE, 10),
                     "knn_features_target": c0.time_stage(capi.STAGE_KNN_TARGET, 3)}
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -322,10 +447,9 @@ def run_b200(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (ms_nn * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of nn_search_kernel, first launch of a pair (full 12-D
-                    # search of every query), ncu --set full capture summarised in profiles/r1_summary_v5.md
-                    "traffic": NCU_TRAFFIC_BYTES,
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "kernel": "SE(3) correspondence stage: nn_filter_kernel + nn_search_kernel",
                     "algorithmic_bytes": alg_bytes, "kernel_ms": ms_nn, "launches_averaged": se3_launches,
                     "peak_source": peak_src, "queries_per_s": n / (ms_nn * 1e-3),
@@ -350,6 +474,12 @@ def run_b200(args):
                                  "transl": float(np.linalg.norm(T_cpu[:3, 3] - T_dev[0][:3, 3])),
                                  "iterations_cpu": st_cpu.num_iterations, "iterations_gpu": stats[0].num_iterations}}
         cpu["reference_source_build"] = reference_source_build_step(pairs[0], T_dev[0])
+        other_configs = configs_block(capi, orc, local_rank)
+    for c in ctxs:  # free the batch contexts before the large pair
+        c.close()
+    sharded = None
+    if world > 1:
+        sharded = sharded_pair_block(capi, pkg.sharding, torch, dist, local_rank, rank, world)
     if rank == 0:
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -367,10 +497,16 @@ def run_b200(args):
             "accuracy": {"max_rot_err_rad_vs_gt": max(e[0] for e in errs), "max_transl_err_m_vs_gt": max(e[1] for e in errs),
                          "pairs_within_2deg_0.25m": int(sum(1 for e in errs if np.degrees(e[0]) <= 2.0 and e[1] <= 0.25)),
                          "pairs": P},
-            "contexts_per_gpu": args.contexts, "loop": "one CUDA graph per pair (conditional WHILE node)",
+            "contexts_per_gpu": args.contexts,
+            "loop": "one CUDA graph launch per pair (conditional WHILE node; executable kept per context, "
+                    "%d instantiation(s) on context 0 over the whole run)" % int(stats[0].graph_instantiations),
         }
-    for c in ctxs:
-        c.close()
+        if world == 1:
+            result["configs"] = other_configs
+        else:
+            result["sharded_pair"] = sharded
+            result["note_vs_reference"] = ("--impl reference runs ONE host process; a ratio of this line's value to it "
+                                           "compares %d GPUs with one CPU arm, not a per-GPU speed-up" % world)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

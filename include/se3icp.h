@@ -180,12 +180,15 @@ int se3icp_run_sequence(se3icp_ctx* ctx, const double* const* scans, const size_
 int se3icp_comm_unique_id(void* id_out);
 int se3icp_comm_init(se3icp_ctx* ctx, int n_ranks, int rank, const void* id);
 int se3icp_comm_destroy(se3icp_ctx* ctx);
+/* rank / size of the communicator the context currently holds (0 / 1 without one) */
+int se3icp_comm_info(se3icp_ctx* ctx, int* rank_out, int* n_ranks_out);
 int se3icp_run_sharded(se3icp_ctx* ctx, const se3icp_params* p, size_t src_begin, size_t src_end, void* nccl_comm,
                        int rank, int n_ranks, double* T_out, se3icp_stats* stats);
 
 /* measurement hook (bench.py roofline): re-launches one kernel of the hot path `repeats` times on the
- * context's stream, on the device data left by the last se3icp_run, and returns the average launch
- * duration measured with CUDA events on that stream. */
+ * context's stream, on the device data left by the last se3icp_run (at its final pose), and returns the average
+ * launch duration measured with CUDA events on that stream.  The two searches are timed COLD: every query, no
+ * remembered match, no coherence shortcut.  The context's correspondences are overwritten. */
 enum se3icp_stage { SE3ICP_STAGE_NN_SE3 = 0, SE3ICP_STAGE_NN_XYZ = 1, SE3ICP_STAGE_REDUCE = 2, SE3ICP_STAGE_KNN_TARGET = 3 };
 int se3icp_time_stage(se3icp_ctx* ctx, int stage, int repeats, double* ms_avg);
 

@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "se3icp_synchronize", "se3icp_set_cloud", "se3icp_set_cloud_device", "se3icp_run", "se3icp_run_async",
     "se3icp_run_finish", "se3icp_get_history", "se3icp_get_correspondences", "se3icp_get_se3_cloud",
     "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_swap_clouds", "se3icp_run_sequence", "se3icp_run_sharded", "se3icp_comm_unique_id", "se3icp_comm_init",
-    "se3icp_comm_destroy", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
+    "se3icp_comm_destroy", "se3icp_comm_info", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
     "se3icp_normals", "se3icp_gicp_cov", "se3icp_nn_se3", "se3icp_nn_xyz", "se3icp_trim", "se3icp_reduce_pt2pt",
     "se3icp_reduce_pt2pl", "se3icp_reduce_gicp", "se3icp_solve",
 ]
@@ -260,6 +260,12 @@ class Context:
 
     def comm_destroy(self):
         _check(lib().se3icp_comm_destroy(self._h))
+
+    def comm_info(self):
+        """(rank, n_ranks) of the communicator the library holds for this context"""
+        r, n = C.c_int(0), C.c_int(0)
+        _check(lib().se3icp_comm_info(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
 
     def run_sharded(self, params, src_begin, src_end, nccl_comm=None, rank=0, n_ranks=1):
         T = np.zeros((4, 4))

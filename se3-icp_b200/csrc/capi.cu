@@ -949,6 +949,13 @@ int se3icp_comm_destroy(se3icp_ctx* c) {
     return SE3ICP_OK;
 }
 
+int se3icp_comm_info(se3icp_ctx* c, int* rank_out, int* n_ranks_out) {
+    SE3_TRY(check_ctx(c));
+    if (rank_out) *rank_out = c->comm ? c->comm_rank : 0;
+    if (n_ranks_out) *n_ranks_out = c->comm ? c->comm_size : 1;
+    return SE3ICP_OK;
+}
+
 int se3icp_run_sharded(se3icp_ctx* c, const se3icp_params* p, size_t src_begin, size_t src_end, void* nccl_comm,
                        int rank, int n_ranks, double* T_out, se3icp_stats* stats) {
     SE3_TRY(check_ctx(c));
@@ -1007,6 +1014,8 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
     for (int r = -1; r < repeats; r++) {  // r == -1 is a warm-up launch
         if (stage == SE3ICP_STAGE_NN_SE3)
             SE3_CUDA(cudaMemsetAsync(&c->dstate()->repair_count, 0, sizeof(int), st));
+        if (stage == SE3ICP_STAGE_NN_SE3 || stage == SE3ICP_STAGE_NN_XYZ)  // cold search: no remembered matches
+            SE3_CUDA(cudaMemsetAsync(c->corr_idx.ptr, 0xff, c->n[0] * sizeof(int), st));
         SE3_CUDA(cudaEventRecord(e0, st));
         switch (stage) {
             case SE3ICP_STAGE_NN_SE3:

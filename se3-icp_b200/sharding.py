@@ -16,6 +16,22 @@ def shard_range(n, world, rank):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def dealt_order(n, world, block=4096):
+    """Permutation that deals `n` points to `world` ranks in blocks of `block` consecutive points and lays every rank's
+    share out contiguously: after `cloud[dealt_order(n, world)]` the contiguous range shard_range(n, world, r) of rank r
+    holds the blocks r, r + world, r + 2 world, ... of the original order.  A scan is ordered by image row or by laser
+    ring, so plain contiguous ranges give the ranks different parts of the scene and different search costs; dealing
+    the blocks out balances them while se3icp_run_sharded still gets one contiguous range per rank.  (A point cloud is
+    an unordered set: the registration result does not depend on the order beyond summation order.)"""
+    n, world, block = int(n), int(world), int(block)
+    if world <= 1:
+        return np.arange(n, dtype=np.int64)
+    blocks = np.arange((n + block - 1) // block, dtype=np.int64)
+    dealt = np.concatenate([blocks[r::world] for r in range(world)])
+    idx = (dealt[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).reshape(-1)
+    return idx[idx < n]
+
+
 def pairs_of_rank(n_pairs, world, rank):
     """indices of the independent pairs owned by `rank` (round robin, as SURVEY §8e)"""
     return list(range(rank, n_pairs, world))

@@ -60,6 +60,25 @@ def test_shard_range_partitions(pkg):
     assert sorted(sum((sh.pairs_of_rank(256, 8, k) for k in range(8)), [])) == list(range(256))
 
 
+def test_dealt_order_balances_contiguous_ranges(pkg):
+    """dealt_order is a permutation, and after it every rank's contiguous range is a regular sample of the whole cloud"""
+    sh = pkg.sharding
+    for n, world, block in ((0, 2, 4), (10, 4, 4), (20_000, 3, 4096), (1_000_003, 8, 4096)):
+        p = sh.dealt_order(n, world, block)
+        assert p.shape == (n,) and np.array_equal(np.sort(p), np.arange(n))
+    np.testing.assert_array_equal(sh.dealt_order(37, 1), np.arange(37))
+    n, world, block = 1_000_003, 8, 4096
+    p = sh.dealt_order(n, world, block)
+    for r in range(world):
+        b, e = sh.shard_range(n, world, r)
+        share = p[b:e]
+        # the original positions of a rank's share spread over the whole cloud: every eighth of the cloud holds ~1/8 of them
+        hist = np.histogram(share, bins=8, range=(0, n))[0]
+        assert hist.min() > 0.8 * len(share) / 8 and hist.max() < 1.2 * len(share) / 8
+        # and they come in runs of consecutive points (memory order inside a block is kept)
+        assert np.mean(np.diff(share) == 1) > 0.99
+
+
 def test_world2_gloo(tmp_path):
     world = 2
     port = 29500 + (os.getpid() % 2000)

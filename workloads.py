@@ -231,6 +231,54 @@ def rgbd_pair(seed=0, width=640, height=480, f=525.0, stride=1):
     return src, tgt, step
 
 
+def rgbd_pair_device(seed=0, width=4096, height=3072, f=525.0 * 6.4, device="cuda"):
+    """rgbd_pair() rendered on the GPU with torch, for the one configuration whose host-side generation takes a
+    minute (BASELINE.json configs[4]: ~10 M points per cloud).  Same scene, poses and noise model; the noise samples
+    come from torch's generator, so the clouds are not those of rgbd_pair().  Returns (src, tgt, T_gt) with the
+    clouds as contiguous (n, 3) float64 CUDA tensors."""
+    import torch
+    rng = np.random.default_rng(2000 + seed)
+    room = np.array([-2.5, -1.4, -0.5, 2.5, 1.4, 3.7])
+    boxes = []
+    for _ in range(10):
+        cx, cz = rng.uniform(-2.0, 2.0), rng.uniform(1.2, 3.2)
+        w, h, d = rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.2), rng.uniform(0.3, 0.9)
+        boxes.append((cx - w / 2, 1.4 - h, cz - d / 2, cx + w / 2, 1.4, cz + d / 2))
+    pose0 = make_T(rot_3d(rng.uniform(-0.05, 0.05), rng.uniform(-0.2, 0.2), rng.uniform(-0.03, 0.03)),
+                   [rng.uniform(-0.5, 0.5), rng.uniform(-0.2, 0.2), rng.uniform(-0.3, 0.2)])
+    step = make_T(rot_3d(rng.uniform(-0.03, 0.03), rng.uniform(-0.08, 0.08), rng.uniform(-0.03, 0.03)),
+                  rng.uniform(-0.08, 0.08, 3))
+    gen = torch.Generator(device=device)
+    gen.manual_seed(2000 + seed)
+    f64 = dict(dtype=torch.float64, device=device)
+    u = (torch.arange(width, **f64) - width / 2 + 0.5) / f
+    v = (torch.arange(height, **f64) - height / 2 + 0.5) / f
+    d_c = torch.stack([u[None, :].expand(height, width), v[:, None].expand(height, width),
+                       torch.ones(height, width, **f64)], -1).reshape(-1, 3)
+
+    def slab(box, o, inv):
+        lo = (torch.tensor(box[:3], **f64) - o) * inv
+        hi = (torch.tensor(box[3:], **f64) - o) * inv
+        return torch.minimum(lo, hi).amax(1), torch.maximum(lo, hi).amin(1)
+
+    def cast(pose):
+        o = torch.tensor(pose[:3, 3], **f64)
+        inv = 1.0 / (d_c @ torch.tensor(pose[:3, :3].T.copy(), **f64))
+        _, best = slab(room, o, inv)  # inside the room: exit distance of the room box
+        for b in boxes:
+            tmin, tmax = slab(b, o, inv)
+            hit = (tmax >= tmin) & (tmin > 0) & (tmin < best)
+            best = torch.where(hit, tmin, best)
+        z = best
+        z = z + torch.randn(z.shape, generator=gen, **f64) * (0.002203 * z * z - 0.001028 * z + 0.0005351)
+        ok = (z > 0.4) & (z < 4.0)
+        return (d_c[ok] * z[ok, None]).contiguous()
+
+    tgt = cast(pose0)
+    src = cast(pose0 @ step)
+    return src, tgt, step
+
+
 LOUNGE_PARAMS = dict(estimated_overlap=0.75, mse_switch_error=5e-5, max_num_se3_iterations=10,
                      number_of_nn_for_LRF=90)  # benchmark_lounge.cpp:183-186
 
