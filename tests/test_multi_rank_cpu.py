@@ -74,7 +74,7 @@ def test_dealt_order_balances_contiguous_ranges(pkg):
         share = p[b:e]
         # the original positions of a rank's share spread over the whole cloud: every eighth of the cloud holds ~1/8 of them
         hist = np.histogram(share, bins=8, range=(0, n))[0]
-        assert hist.min() > 0.8 * len(share) / 8 and hist.max() < 1.2 * len(share) / 8
+        assert hist.min() > 0.7 * len(share) / 8 and hist.max() < 1.3 * len(share) / 8  # one 4096-point block is a quarter of a bin
         # and they come in runs of consecutive points (memory order inside a block is kept)
         assert np.mean(np.diff(share) == 1) > 0.99
 
