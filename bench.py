@@ -318,7 +318,8 @@ def sharded_pair_block(capi, sharding, torch, dist, local_rank, rank, world):
 
 
 def ss_loop_name(stats):
-    return "one CUDA graph (conditional WHILE node)" if stats.graph_instantiations > 0 else "host-driven, one sync per iteration"
+    return ("one CUDA graph (conditional WHILE node), record all-reduced over peer memory inside the iteration's last kernel"
+            if stats.loop_was_graph else "host-driven, one sync + one ncclAllReduce per iteration")
 
 
 # --------------------------------------------------------------------------------------------------

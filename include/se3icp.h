@@ -108,6 +108,9 @@ typedef struct se3icp_stats {
     int64_t graph_instantiations;    /* loop-graph executables this context has created so far (it keeps one and
                                         re-parameterises it from run to run; a count that grows with the runs means the
                                         launch sequence keeps changing) */
+    int64_t loop_was_graph;          /* 1 = this run's iteration loop was one CUDA graph launch; 0 = host-driven (one
+                                        synchronisation per iteration: use_graph = 0, a process under Nsight Compute, or a
+                                        sharded pair that all-reduces through NCCL) */
 } se3icp_stats;
 
 typedef struct se3icp_ctx se3icp_ctx;

@@ -69,6 +69,7 @@ class Stats(C.Structure):
         ("feature_reuses", C.c_int64),
         ("queries_searched", C.c_int64),
         ("graph_instantiations", C.c_int64),
+        ("loop_was_graph", C.c_int64),
     ]
 
 

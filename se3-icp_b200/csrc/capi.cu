@@ -231,6 +231,72 @@ int alloc_run(se3icp_ctx* c) {
         }                                                                                     \
     } while (0)
 
+// ---- peer-memory mailboxes of the sharded pair -------------------------------------------------------------------
+void peer_teardown(se3icp_ctx* c) {
+    for (int r = 0; r < kMaxPeers; r++) {
+        if (c->peer_ptr[r] && r != c->comm_rank) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+        c->peer_ptr[r] = nullptr;
+    }
+    c->peer_ready = false;
+}
+
+// Every rank allocates its mailbox, the CUDA IPC handles travel through one ncclAllGather on the communicator the
+// context already holds, and every rank maps the others' mailboxes (NVLink peer access).  Not fatal when it fails
+// (GPUs without peer access, ranks on different nodes): the run then all-reduces through NCCL from a host-driven loop.
+int peer_setup(se3icp_ctx* c) {
+    peer_teardown(c);
+    static const bool disabled = [] {
+        const char* e = getenv("SE3ICP_SHARDED_P2P");
+        return e && atoi(e) == 0;
+    }();
+    const int world = c->comm_size;
+    if (disabled || !c->comm || world < 2 || world > kMaxPeers) return 0;
+    const NcclApi* nccl = nccl_api();
+    if (!nccl) return 0;
+    cudaStream_t st = c->stream;
+    const size_t box_bytes = (size_t)2 * world * kPeerSlotWords * sizeof(unsigned long long);
+    SE3_TRY(c->mailbox.ensure(box_bytes));
+    SE3_TRY(c->mailbox_table.ensure((size_t)kMaxPeers * sizeof(void*)));
+    SE3_TRY(c->scratch.ensure((size_t)(world + 1) * sizeof(cudaIpcMemHandle_t)));
+    SE3_CUDA(cudaMemsetAsync(c->mailbox.ptr, 0, c->mailbox.cap, st));
+    cudaIpcMemHandle_t mine;
+    SE3_CUDA(cudaIpcGetMemHandle(&mine, c->mailbox.ptr));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    char* d_mine = c->scratch.as<char>();
+    char* d_all = d_mine + sizeof(cudaIpcMemHandle_t);
+    SE3_CUDA(cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    SE3_NCCL(nccl->AllGather(d_mine, d_all, sizeof(mine), ncclChar, (ncclComm_t)c->comm, st));
+    SE3_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)world * sizeof(mine), cudaMemcpyDeviceToHost, st));
+    SE3_CUDA(cudaStreamSynchronize(st));  // also: every rank's mailbox is zeroed before anyone can write into it ...
+    bool ok = true;
+    for (int r = 0; r < world && ok; r++) {
+        if (r == c->comm_rank) {
+            c->peer_ptr[r] = c->mailbox.ptr;
+        } else if (cudaIpcOpenMemHandle(&c->peer_ptr[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            c->peer_ptr[r] = nullptr;
+            ok = false;
+        }
+    }
+    // ... which the second collective guarantees: nobody leaves it before everybody has passed the synchronize above.
+    // It also agrees on the outcome: one rank without peer access sends everybody to the NCCL path.
+    int* d_ok = reinterpret_cast<int*>(d_mine);
+    int h_ok = ok ? 1 : 0;
+    SE3_CUDA(cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    SE3_NCCL(nccl->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, (ncclComm_t)c->comm, st));
+    SE3_CUDA(cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SE3_CUDA(cudaStreamSynchronize(st));
+    if (!h_ok) {
+        peer_teardown(c);
+        return 0;
+    }
+    SE3_CUDA(cudaMemcpyAsync(c->mailbox_table.ptr, c->peer_ptr, (size_t)kMaxPeers * sizeof(void*), cudaMemcpyHostToDevice, st));
+    SE3_CUDA(cudaStreamSynchronize(st));
+    c->peer_ready = true;
+    c->peer_runs = 0;
+    return 0;
+}
+
 int enqueue_setup(se3icp_ctx* c) {
     const RunConfig& cfg = c->cfg;
     const se3icp_params& p = c->params;
@@ -358,8 +424,8 @@ int enqueue_iteration(se3icp_ctx* c, unsigned long long cond_handle = 0) {
     TargetView T = c->target_view();
     CorrBuffers cb = c->corr_buffers(false);
     IterState* ds = c->dstate();
-    SE3_TRY(launch_nn_filter(S, T, cfg, ds, cb, st));
-    if (cfg.coherence || cfg.coherence_xyz) c->launches += 1;
+    SE3_TRY(launch_nn_filter(S, T, cfg, ds, cb, st));  // seeds the first pass of a run, then the coherence filter
+    c->launches += 1;
     const int mode = c->params.nn_mode;
     if (cfg.has_se3 && (mode == SE3ICP_NN_BRUTE_F32 || mode == SE3ICP_NN_EXACT_F64)) {
         SE3_TRY(launch_nn_se3_brute(S, T, cfg, ds, cb, mode == SE3ICP_NN_EXACT_F64, st));
@@ -403,16 +469,25 @@ int enqueue_iteration(se3icp_ctx* c, unsigned long long cond_handle = 0) {
             c->launches += 6;
         }
     }
-    // single GPU: the last block of the reduction also solves, updates and decides (an iteration ends with this launch)
+    // The last block of the reduction also solves, updates and decides (an iteration ends with this launch): always on
+    // one GPU, and for a sharded pair whenever the ranks can all-reduce the record over peer memory inside that block.
+    const bool p2p = multi && c->peer_ready && !(cfg.trim_active && cfg.n_keep_target > 0);  // (trimming: NCCL histograms)
     SolveFusion fuse{};
-    fuse.enabled = !multi;
+    fuse.enabled = !multi || p2p;
+    fuse.peer.world = 1;
+    if (p2p) {
+        fuse.peer.mailboxes = c->mailbox_table.as<unsigned long long*>();
+        fuse.peer.world = c->comm_size;
+        fuse.peer.rank = c->comm_rank;
+        fuse.peer.seq_base = c->peer_runs << 32;
+    }
     fuse.history = c->history.as<double>();
     fuse.hist = cb.thist ? nullptr : c->hist.as<unsigned int>();
     fuse.cond_handle = cond_handle;
     SE3_TRY(launch_reduce(S, T, cfg, ds, cb, c->partials.as<double>(), fuse, st));
     c->launches += 1;
-    if (multi) {
-        // one all-reduce of the 29-double record per iteration; every rank then runs the identical solve
+    if (multi && !p2p) {
+        // NCCL path: one all-reduce of the 29-double record per iteration; every rank then runs the identical solve
         SE3_TRY(launch_sum_partials(c->partials.as<double>(), c->totals.as<double>(), st));
         SE3_NCCL(nccl->AllReduce(c->totals.ptr, c->totals.ptr, kReducePartials, ncclFloat64, ncclSum, comm, st));
         SE3_TRY(launch_solve_update(cfg, ds, c->totals.as<double>(), 1, c->history.as<double>(), c->hist.as<unsigned int>(),
@@ -591,6 +666,7 @@ int se3icp_destroy(se3icp_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) se3icp_comm_destroy(c);
+    peer_teardown(c);
     release_loop_graph(c);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -703,7 +779,9 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
     // Iterations: the stop/phase decision lives on the device (tail of reduce_kernel).
     c->graph_run = false;
     const bool multi_rank = c->sharded && c->comm && c->comm_size > 1;
-    if (want_graph(p) && !multi_rank) {
+    const bool p2p = multi_rank && c->peer_ready && !(c->cfg.trim_active && c->cfg.n_keep_target > 0);
+    if (multi_rank) c->peer_runs += 1;  // collective call: the same count on every rank -> unique sequence words
+    if (want_graph(p) && (!multi_rank || p2p)) {
         // The whole loop is ONE graph launch: a conditional WHILE node whose body is the captured iteration;
         // its last kernel sets the condition from the device-side done flag.  The host never round-trips.
         SE3_TRY(build_loop_graph(c));
@@ -736,6 +814,11 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
     }
     c->run_pending = false;  // whatever happens below, the context accepts calls again
     SE3_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_state->peer_timeout) {
+        set_last_error("sharded pair: the record of a peer rank did not arrive within 20 s (rank %d of %d)", c->comm_rank,
+                       c->comm_size);
+        return SE3ICP_ERR_NCCL;
+    }
     const IterState& hs = *c->h_state;
     if (T_out) memcpy(T_out, hs.T_final, 16 * sizeof(double));
     if (stats) {
@@ -756,6 +839,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         stats->feature_reuses = c->feature_reuses;
         stats->queries_searched = (long long)hs.searched_total;
         stats->graph_instantiations = c->graph_instantiations;
+        stats->loop_was_graph = c->graph_run ? 1 : 0;
     }
     return SE3ICP_OK;
 }
@@ -933,11 +1017,14 @@ int se3icp_comm_init(se3icp_ctx* c, int n_ranks, int rank, const void* id) {
     c->comm_owned = true;
     c->comm_rank = rank;
     c->comm_size = n_ranks;
+    SE3_TRY(peer_setup(c));  // collective, like the communicator itself
     return SE3ICP_OK;
 }
 
 int se3icp_comm_destroy(se3icp_ctx* c) {
     SE3_TRY(check_ctx(c));
+    cudaStreamSynchronize(c->stream);
+    peer_teardown(c);
     if (c->comm && c->comm_owned) {
         const NcclApi* nccl = nccl_api();
         if (nccl) nccl->CommDestroy((ncclComm_t)c->comm);
@@ -963,12 +1050,13 @@ int se3icp_run_sharded(se3icp_ctx* c, const se3icp_params* p, size_t src_begin, 
         set_last_error("bad source range [%zu, %zu) of %zu", src_begin, src_end, c->n[0]);
         return SE3ICP_ERR_ARG;
     }
-    if (nccl_comm) {  // caller-owned communicator
-        if (c->comm && c->comm_owned) se3icp_comm_destroy(c);
+    if (nccl_comm && nccl_comm != c->comm) {  // caller-owned communicator, first use
+        if (c->comm) se3icp_comm_destroy(c);
         c->comm = nccl_comm;
         c->comm_owned = false;
         c->comm_rank = rank;
         c->comm_size = n_ranks;
+        SE3_TRY(peer_setup(c));
     }
     if (!c->comm && (src_begin != 0 || src_end != c->n[0])) {
         set_last_error("a partial source range needs a communicator (se3icp_comm_init)");
@@ -1019,12 +1107,15 @@ int se3icp_time_stage(se3icp_ctx* c, int stage, int repeats, double* ms_avg) {
         SE3_CUDA(cudaEventRecord(e0, st));
         switch (stage) {
             case SE3ICP_STAGE_NN_SE3:
-                if (c->params.nn_mode == SE3ICP_NN_BRUTE_F32 || c->params.nn_mode == SE3ICP_NN_EXACT_F64)
+                if (c->params.nn_mode == SE3ICP_NN_BRUTE_F32 || c->params.nn_mode == SE3ICP_NN_EXACT_F64) {
                     SE3_TRY(launch_nn_se3_brute(S, T, cfg, c->dstate(), cb, 0, st));
-                else
+                } else {  // cold pass = seeding (nn_filter_kernel) + search
+                    SE3_TRY(launch_nn_filter(S, T, cfg, c->dstate(), cb, st));
                     SE3_TRY(launch_nn_se3_tree(S, T, cfg, c->dstate(), cb, st));
+                }
                 break;
             case SE3ICP_STAGE_NN_XYZ:
+                SE3_TRY(launch_nn_filter(S, T, cfg, c->dstate(), cb, st));
                 SE3_TRY(launch_nn_xyz(S, T, cfg, c->dstate(), cb, st));
                 break;
             case SE3ICP_STAGE_REDUCE:
@@ -1286,6 +1377,7 @@ int se3icp_nn_se3(se3icp_ctx* c, const double* src_rows, size_t n, const double*
     switch (nn_mode) {
         case SE3ICP_NN_AUTO:
         case SE3ICP_NN_TREE:
+            SE3_TRY(launch_nn_filter(S, T, cfg, c->dstate(), cb, c->stream));  // seeds every query
             SE3_TRY(launch_nn_se3_tree(S, T, cfg, c->dstate(), cb, c->stream));
             break;
         case SE3ICP_NN_BRUTE_F32:
@@ -1328,6 +1420,7 @@ int se3icp_nn_xyz(se3icp_ctx* c, const double* queries, size_t n, const double* 
     identity_config(cfg, SE3ICP_PT2PT, false);
     SE3_TRY(stage_corr_alloc(c, n));
     CorrBuffers cb = c->corr_buffers(true);
+    SE3_TRY(launch_nn_filter(S, T, cfg, c->dstate(), cb, c->stream));  // seeds every query
     SE3_TRY(launch_nn_xyz(S, T, cfg, c->dstate(), cb, c->stream));
     SE3_CUDA(cudaMemcpyAsync(idx, cb.idx, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (d2) SE3_CUDA(cudaMemcpyAsync(d2, cb.d2_nd, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

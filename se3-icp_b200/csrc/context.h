@@ -33,6 +33,12 @@ struct se3icp_ctx {
     int comm_rank = 0, comm_size = 1;
     bool sharded = false;
     int shard_begin = 0, shard_end = 0;
+    // peer-memory all-reduce of the sharded pair (internal.h: PeerReduce): own mailbox, the peers' mailboxes opened
+    // through CUDA IPC, the device array of all of them, and the run counter that makes sequence words unique
+    se3::DeviceBuf mailbox, mailbox_table;
+    void* peer_ptr[se3::kMaxPeers] = {nullptr};
+    bool peer_ready = false;
+    unsigned long long peer_runs = 0;
 
     // What frame[w] / nrm[w] / cov[w] currently hold: the neighbourhood features of the cloud in slot w are invariant
     // under the per-pair normalisation (uniform scale about the cloud's own centroid), so a scan that was the source of

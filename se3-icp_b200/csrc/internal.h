@@ -63,7 +63,7 @@ struct IterState {
     unsigned int thr_bits;  // trimmed rejection: key of the n_keep-th correspondence (float bits, complemented when keeping the largest)
     int eq_budget;          // ... how many of the correspondences whose key equals thr_bits survive
     int tie_limit;          // ... which: those with source index <= tie_limit (index order, like the mask kernels)
-    int pad0_;
+    int peer_timeout;       // sharded pair: a peer's record did not arrive within kPeerTimeoutNs (run aborted)
     int repair_count;
     int hist_count;
     int switch_iter;  // value of iter when the ICP phase began (-1 before)
@@ -202,9 +202,24 @@ int launch_trim_count_eq(const RunConfig& cfg, IterState* state, const float* di
                          int* block_eq, int* eq_total, cudaStream_t st);
 int launch_trim_apply(const RunConfig& cfg, IterState* state, const float* distf, int n, const unsigned int* hist,
                       const int* block_eq, const int* rank_eq, int rank, uint8_t* keep, cudaStream_t st);
+// One very large pair sharded over the GPUs of a node: the per-iteration all-reduce of the 29-double normal-equation
+// record runs INSIDE the iteration's last kernel over peer memory (NVLink / NVSwitch).  Every rank owns a mailbox of
+// kPeerSlotWords-word slots [2 parities][world]; the last block of reduce_kernel stores its rank's record into slot
+// [parity][rank] of every peer's mailbox, publishes it with a sequence word, waits until the world's records of this
+// iteration have arrived in its own mailbox and sums them in rank order — identical bits on every rank, no host
+// round trip, no library call, and the loop stays one CUDA graph.
+constexpr int kPeerSlotWords = 32;  // 31 doubles of record + 1 sequence word (256 bytes)
+constexpr int kMaxPeers = 16;
+struct PeerReduce {
+    unsigned long long* const* mailboxes;  // device array [world]: every rank's mailbox, peer-mapped (own entry: local)
+    int world, rank;                       // world <= 1: no exchange
+    unsigned long long seq_base;           // run counter << 32 (identical on all ranks); sequence = seq_base + iteration
+};
+
 // the tail of an iteration folded into reduce_kernel (its last block to finish runs the solve / update / stop logic)
 struct SolveFusion {
     int enabled;
+    PeerReduce peer;
     double* history;                 // per-iteration T_i or null
     unsigned int* hist;              // histograms of the multi-pass trim to clear for the next iteration, or null
     unsigned long long cond_handle;  // cudaGraphConditionalHandle of the loop graph, 0 = none

@@ -260,15 +260,18 @@ int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConf
 }
 
 // ------------------------------------------------------------------------------------------------
-// Coherence filter, one THREAD per query (coalesced plane loads): settles every query whose remembered
-// match is provably still its unique nearest neighbour and appends the others to the work list that the
-// warp-per-query search kernels consume.  Runs before both searches; a no-op in non-coherent iterations.
+// Per-query preparation of a correspondence pass, one THREAD per query (coalesced plane loads), run before both searches:
+//  * seeding — a query without a remembered match (first iteration of a run) gets the target row whose Morton key is
+//    closest to its own as a stand-in "previous match": key construction and the 17-step binary search run once per
+//    thread here instead of 32-fold redundantly in every lane of the warp-per-query search kernel, which then has a
+//    single, warm-started code path;
+//  * coherence filter — settles every query whose remembered match is provably still its unique nearest neighbour and
+//    appends the others to the work list the search kernels consume.
 __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                          IterState* __restrict__ state, CorrBuffers cb) {
     if (state->done) return;
     const bool se3 = se3_phase_active(cfg, state);
-    const bool enabled = se3 ? cfg.coherence : cfg.coherence_xyz;
-    if (!enabled || !(state->T_change < cfg.coherence_thr)) return;
+    const bool enabled = (se3 ? cfg.coherence : cfg.coherence_xyz) && state->T_change < cfg.coherence_thr;
     const int t = S.begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S.end) return;
     // spatially sorted processing order: the work list then hands neighbouring queries to neighbouring warps
@@ -276,7 +279,49 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
     const double* Tm = state->T_total;
     const size_t n = (size_t)S.n, m = (size_t)T.n;
     bool settled = false;
-    const int prev = cb.idx[i];
+    int prev = cb.idx[i];
+    // first ICP-phase pass after the SE(3) phase: the remembered match is the 12-D one, whose position may be far from
+    // the query; the better of it and a fresh Morton seed becomes the starting point
+    const bool reseed = !se3 && cfg.has_se3 && state->iter == state->switch_iter;
+    if (prev < 0 || prev >= T.n || reseed) {  // seed from the Morton order of the search structure
+        int lo = 0, hi = T.n;
+        if (se3) {
+            double q[12];
+            make_query(S, cfg, Tm, i, q);
+            double Ru[9];
+            const double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
+            const double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
+            const uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= T.n) lo = T.n - 1;
+            prev = T.perm12[lo];
+        } else {
+            const double px = S.x[i], py = S.y[i], pz = S.z[i];
+            const double qx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3], qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7],
+                         qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
+            const uint64_t key = morton63(qx, qy, qz, T.idx.bbox);
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (T.idx.keys[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= T.n) lo = T.n - 1;
+            const int seed = T.idx.perm[lo];
+            if (prev >= 0 && prev < T.n &&
+                sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]) <=
+                    sqdist3(qx, qy, qz, T.idx.x[seed], T.idx.y[seed], T.idx.z[seed])) {
+                // the 12-D match is at least as close: keep it
+            } else {
+                prev = seed;
+            }
+        }
+        cb.idx[i] = prev;  // (a seed carries no certificate: ref_d2nd[i] is still "not known" from the set-up)
+    }
+    if (!enabled) return;
     const double dref = cb.ref_d2nd[i];
     // the first ICP-phase iteration still sees the 12-D references of the SE(3) phase: ignore them once
     const bool refs_match_space = se3 || !(cfg.has_se3 && state->iter == state->switch_iter);
@@ -316,7 +361,6 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
 
 int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                      cudaStream_t st) {
-    if (!cfg.coherence && !cfg.coherence_xyz) return 0;
     int g = (S.end - S.begin + 255) / 256;
     if (g < 1) g = 1;
     nn_filter_kernel<<<g, 256, 0, st>>>(S, T, cfg, state, cb);
@@ -457,30 +501,13 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
         }
     };
 
+    // warm start: every query has a remembered match, or the stand-in nn_filter_kernel seeded from the Morton order
     if (have_prev && !coherent) {
         best_j = T.inv12[prev];
         best_id = prev;
         tau = exact_d2_12_sm(q, T.rows64, m, best_j);
-    } else {
-        int first;
-        if (have_prev) {
-            first = T.inv12[prev] >> 5;  // the remembered match's own leaf: best and a first runner-up
-        } else {
-            // no warm start: the leaf around the query's own 6-D key gives the first radius
-            double Ru[9];
-            double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
-#pragma unroll
-            for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
-            double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
-            uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
-            int lo = 0, hi = M;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
-            }
-            if (lo >= M) lo = M - 1;
-            first = lo >> 5;
-        }
+    } else if (have_prev) {
+        const int first = T.inv12[prev] >> 5;  // the remembered match's own leaf: best and a first runner-up
         leaf_fn(first);
         skip_leaf = first;
     }
@@ -569,24 +596,11 @@ __device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& 
         tau = sqdist3(qx, qy, qz, I.x[prev], I.y[prev], I.z[prev]);
         best = prev;
     }
-    // ... plus one whole leaf whenever a runner-up is needed: the previous match's own leaf (one load), or, when
-    // there is no previous match or it may be far (cold start, first iteration after the SE(3) phase), the leaf
-    // holding the query's own Morton code (a binary search: ~17 dependent loads, paid once per run)
-    const bool after_switch = cfg.has_se3 && state->iter == state->switch_iter;
-    if (coherent || !have_prev || after_switch) {
-        int first;
-        if (have_prev && !after_switch) {
-            first = I.inv[prev] >> 5;
-        } else {
-            uint64_t key = morton63(qx, qy, qz, I.bbox);
-            int lo = 0, hi = I.n;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (I.keys[mid] < key) lo = mid + 1; else hi = mid;
-            }
-            if (lo >= I.n) lo = I.n - 1;
-            first = lo >> 5;
-        }
+    // ... plus its whole leaf (one load finds it) whenever a runner-up is needed.  Every query has a previous match:
+    // nn_filter_kernel seeds the first pass of a run from the Morton order, and the first ICP-phase pass starts from
+    // the SE(3) phase's match, which is close in position as well.
+    if (coherent && have_prev) {
+        const int first = I.inv[prev] >> 5;
         leaf_fn(first);
         skip_leaf = first;
     }

@@ -66,7 +66,7 @@ __global__ void init_state_kernel(IterState* st, unsigned int* hist) {
         st->thr_bits = 0;
         st->eq_budget = 0;
         st->tie_limit = 0x7fffffff;
-        st->pad0_ = 0;
+        st->peer_timeout = 0;
         st->repair_count = 0;
         st->hist_count = 0;
         st->switch_iter = -1;
@@ -679,10 +679,63 @@ int launch_sum_partials(const double* partials, double* total, cudaStream_t st) 
 // Executed by one whole block of 256 threads: the stand-alone kernel below (sharded pair, stage API) or the last block
 // of reduce_kernel to finish (single-GPU loop).  cond_handle != 0: the caller is the last node of the captured loop
 // body and tells the WHILE node whether to run it again.
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+// All-reduce (sum) of tot[0 .. kAcc) over the ranks of a sharded pair, through the peer-mapped mailboxes (PeerReduce in
+// internal.h).  Called by all 256 threads of one block per rank; returns false when a peer's record did not arrive.
+__device__ bool peer_allreduce_block(const PeerReduce& pr, unsigned long long seq, double* tot /*shared*/, int* s_flag /*shared*/) {
+    const int tid = threadIdx.x, world = pr.world;
+    const int parity = (int)(seq & 1ull);
+    const size_t my_slot = (size_t)(parity * world + pr.rank) * kPeerSlotWords;
+    // (1) my record into slot [parity][rank] of every mailbox (my own included), 8-byte stores over NVLink
+    for (int e = tid; e < world * (kPeerSlotWords - 1); e += blockDim.x) {
+        const int peer = e / (kPeerSlotWords - 1), k = e % (kPeerSlotWords - 1);
+        const double v = k < kAcc ? tot[k] : 0.0;
+        pr.mailboxes[peer][my_slot + k] = (unsigned long long)__double_as_longlong(v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    // (2) publish: the sequence word goes last
+    if (tid < world) {
+        __threadfence_system();  // cumulative: everything the block wrote before the barrier is ordered before the flag
+        volatile unsigned long long* flag = pr.mailboxes[tid] + my_slot + (kPeerSlotWords - 1);
+        *flag = seq;
+    }
+    if (tid == 0) *s_flag = 1;
+    __syncthreads();
+    // (3) wait for the world's records of this iteration in MY mailbox
+    const unsigned long long* mine = pr.mailboxes[pr.rank];
+    if (tid < world) {
+        const volatile unsigned long long* flag = mine + (size_t)(parity * world + tid) * kPeerSlotWords + (kPeerSlotWords - 1);
+        const unsigned long long t0 = global_timer_ns();
+        while (*flag != seq) {
+            if (global_timer_ns() - t0 > kPeerTimeoutNs) {
+                *s_flag = 0;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (!*s_flag) return false;
+    // (4) sum in rank order: the same operations in the same order on every rank
+    if (tid < kAcc) {
+        double s = 0.0;
+        for (int r = 0; r < world; r++) {
+            const volatile unsigned long long* rec = mine + (size_t)(parity * world + r) * kPeerSlotWords;
+            s += __longlong_as_double((long long)rec[tid]);
+        }
+        tot[tid] = s;
+    }
+    __syncthreads();
+    return true;
+}
+
 __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState* __restrict__ gst,
                                                 const double* __restrict__ partials, int n_records,
                                                 double* __restrict__ history, unsigned int* __restrict__ hist,
-                                                unsigned long long cond_handle) {
+                                                unsigned long long cond_handle, const PeerReduce& peer) {
     // The bookkeeping below touches the state ~150 times from one thread; work on a shared-memory copy (one
     // parallel load, one parallel store) instead of a chain of dependent global accesses.
     static_assert(sizeof(IterState) % 8 == 0, "IterState is copied as 64-bit words");
@@ -713,6 +766,18 @@ __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState*
         tot[threadIdx.x] = s;
     }
     __syncthreads();
+    __shared__ int s_peer_ok;
+    if (peer.world > 1) {  // sharded pair: the record becomes the sum over the ranks (block-uniform branch)
+        const unsigned long long seq = peer.seq_base + (unsigned long long)(unsigned int)(st->iter + 1);
+        if (!peer_allreduce_block(peer, seq, tot, &s_peer_ok)) {
+            if (threadIdx.x == 0) {  // abort the run on every rank that sees the time-out; the host reports it
+                gst->peer_timeout = 1;
+                gst->done = 1;
+                if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
+            }
+            return;
+        }
+    }
     __shared__ Ldlt6Shared s_ldlt;
     const bool gauss_newton = cfg.variant != SE3ICP_PT2PT && tot[28] > 0.0;  // block-uniform
     if (gauss_newton) ldlt6_solve_block(tot, s_ldlt);
@@ -816,7 +881,7 @@ __global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterSt
         if (cond_handle && threadIdx.x == 0) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0u);
         return;
     }
-    solve_update_block(cfg, gst, partials, n_records, history, hist, cond_handle);
+    solve_update_block(cfg, gst, partials, n_records, history, hist, cond_handle, PeerReduce{nullptr, 1, 0, 0ull});
 }
 
 // fuse.enabled: the block that finishes last also sums the per-block records (fixed order, so the result does not depend
@@ -971,7 +1036,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) cb.tcount[2] = 0u;  // ready for the next launch
-    solve_update_block(cfg, state, partials, (int)gridDim.x, fuse.history, fuse.hist, fuse.cond_handle);
+    solve_update_block(cfg, state, partials, (int)gridDim.x, fuse.history, fuse.hist, fuse.cond_handle, fuse.peer);
 }
 
 int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,

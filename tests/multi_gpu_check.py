@@ -56,6 +56,8 @@ def main():
         ok = rot < 1e-6 and tr < 1e-6 and ss.num_iterations == s1.num_iterations and same
         report.append("%s/%.1f: rot %.1e transl %.1e it %d/%d identical_across_ranks=%s sharded %.2f ms vs single %.2f ms" %
                       (variant, overlap, rot, tr, ss.num_iterations, s1.num_iterations, same, ss.time_total_ms, s1.time_total_ms))
+        if overlap == 1.0:  # without trimming the record is all-reduced over peer memory and the loop is one graph
+            report[-1] += " loop=%s" % ("graph" if ss.loop_was_graph else "host")
         assert ok, report[-1]
 
     # one large pair (configs[4] style, 1 M points here): sharded vs whole, se3_pt2pl, overlap 1.0

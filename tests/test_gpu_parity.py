@@ -474,8 +474,11 @@ def test_sharded_world1_equals_plain(ctx, capi, bunny4k):
         ctx.run_sharded(p, 0, len(src) // 2)  # partial range without a communicator
 
 
-def test_multi_gpu_sharded_and_batch():
-    """needs >= 2 GPUs (gpurun --gpus 2): sharded pair == single GPU, batch sharding bit-identical"""
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_multi_gpu_sharded_and_batch(p2p):
+    """needs >= 2 GPUs (gpurun --gpus 2): sharded pair == single GPU, batch sharding bit-identical.  Once with the
+    all-reduce inside the iteration's last kernel over peer memory (loop = one CUDA graph), once through NCCL from the
+    host-driven loop (SE3ICP_SHARDED_P2P=0)."""
     import subprocess
     import sys
     import torch
@@ -485,8 +488,9 @@ def test_multi_gpu_sharded_and_batch():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, SE3ICP_SHARDED_P2P=p2p))
     assert "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert ("loop=graph" in r.stdout) == (p2p == "1"), r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("entry_name,variant,overlap", [("RUN_SE3_ICP", "pt2pl", 1.0), ("RUN_SE3_ICP", "gicp", 0.7),
