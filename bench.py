@@ -315,7 +315,7 @@ def sharded_pair_block(capi, sharding, torch, dist, local_rank, rank, world):
                    "transl_vs_1gpu": float(np.linalg.norm(Ts[:3, 3] - T1[:3, 3])),
                    "identical_on_all_ranks": same_on_all_ranks, "loop": ss_loop_name(ss),
                    "search_ms_per_rank": [round(float(x), 2) for x in per_rank.cpu()],
-                   "source_order": "dealt to the ranks in blocks of 4096 points (sharding.dealt_order)",
+                   "source_order": "dealt to the ranks in blocks of 32768 points (sharding.dealt_order)",
                    "timing": "library CUDA events around set-up + loop, max over ranks, best of 2 after a warm-up run"}
         dist.barrier()
     del src, tgt

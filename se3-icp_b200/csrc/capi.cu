@@ -297,6 +297,38 @@ int peer_setup(se3icp_ctx* c) {
     return 0;
 }
 
+// SE3ICP_SETUP_TIMING=1: CUDA events between the stages of the set-up, printed on stderr by se3icp_run_finish
+struct SetupMarks {
+    bool on = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    SetupMarks() {
+        const char* e = getenv("SE3ICP_SETUP_TIMING");
+        on = e && atoi(e) != 0;
+    }
+    void mark(const char* name, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, st);
+        marks.emplace_back(name, ev);
+    }
+    void report(int rank) {
+        if (!on || marks.size() < 2) return;
+        std::string line = "[se3icp] set-up stages (rank " + std::to_string(rank) + "):";
+        for (size_t k = 1; k < marks.size(); k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
+            char buf[96];
+            snprintf(buf, sizeof(buf), " %s %.2f ms;", marks[k].first, ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
+thread_local SetupMarks g_marks;
+
 int enqueue_setup(se3icp_ctx* c) {
     const RunConfig& cfg = c->cfg;
     const se3icp_params& p = c->params;
@@ -306,6 +338,7 @@ int enqueue_setup(se3icp_ctx* c) {
     const double* rt = c->raw_view[1];
     IterState* ds = c->dstate();
 
+    g_marks.mark("begin", st);
     SE3_TRY(launch_init_state(ds, c->hist.as<unsigned int>(), st));
     c->launches += 1;
     if (cfg.has_se3) {
@@ -332,10 +365,12 @@ int enqueue_setup(se3icp_ctx* c) {
                                   c->index[1].z.as<double>(), st));
         c->launches += 2;
     }
+    g_marks.mark("normalise", st);
     SE3_TRY(c->index[1].build(st, &c->launches));
     const bool need_src_index = cfg.has_se3 || cfg.variant == SE3ICP_GICP;
     if (need_src_index) SE3_TRY(c->index[0].build(st, &c->launches));
     c->src_index_built = need_src_index;
+    g_marks.mark("3-D indices", st);
 
     for (int w = 0; w < 2; w++) {
         FeatureArgs fa{};
@@ -366,6 +401,12 @@ int enqueue_setup(se3icp_ctx* c) {
         };
         if (split_target) slice(c->comm_rank, fa.q_begin, fa.q_end);
         if (fa.K <= 0) continue;
+        if (c->sharded) {
+            SE3_TRY(c->knn_list.ensure(c->n[w] * sizeof(int)));
+            SE3_TRY(c->knn_count.ensure(sizeof(int)));
+            fa.active_list = c->knn_list.as<int>();
+            fa.active_count = c->knn_count.as<int>();
+        }
         se3icp_ctx::FeatureKey key;
         key.valid = !(w == 0 && c->sharded);  // a sharded source only holds its own range
         key.n = c->n[w];
@@ -380,6 +421,7 @@ int enqueue_setup(se3icp_ctx* c) {
         c->feat[w].valid = false;
         SE3_TRY(launch_knn_features(c->index[w].view, fa, st));
         c->launches += 1;
+        g_marks.mark(w == 0 ? "kNN/features source" : "kNN/features target", st);
         if (split_target) {
             const NcclApi* nccl = nccl_api();
             if (!nccl) return SE3ICP_ERR_NCCL;
@@ -401,6 +443,7 @@ int enqueue_setup(se3icp_ctx* c) {
                 }
             }
             SE3_NCCL(nccl->GroupEnd());
+            g_marks.mark("target feature exchange", st);
         }
         c->feat[w] = key;
     }
@@ -412,6 +455,7 @@ int enqueue_setup(se3icp_ctx* c) {
     if (cfg.trim_active && cfg.n_keep_target == 0) SE3_CUDA(cudaMemsetAsync(c->keep.ptr, 0, (size_t)N, st));
     SE3_CUDA(cudaMemsetAsync(c->tcount.ptr, 0, kTcountWords * sizeof(unsigned int), st));
     if (cfg.trim_active) SE3_CUDA(cudaMemsetAsync(c->thist.ptr, 0, (size_t)kTrimHistBins * sizeof(unsigned int), st));
+    g_marks.mark("12-D index + resets", st);
     SE3_TRY(launch_mark_loop_start(ds, st));
     c->launches += 1;
     return 0;
@@ -824,6 +868,7 @@ int se3icp_run_finish(se3icp_ctx* c, double* T_out, se3icp_stats* stats) {
         SE3_CUDA(cudaStreamSynchronize(c->stream));
     else
         SE3_CUDA(cudaEventSynchronize(c->ev_end));  // last thing run_async enqueued (after the copy of the state)
+    g_marks.report(c->comm_rank);
     if (c->h_state->peer_timeout) {
         set_last_error("sharded pair: the record of a peer rank did not arrive within 20 s (rank %d of %d)", c->comm_rank,
                        c->comm_size);

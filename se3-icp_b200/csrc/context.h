@@ -36,6 +36,7 @@ struct se3icp_ctx {
     // peer-memory all-reduce of the sharded pair (internal.h: PeerReduce): own mailbox, the peers' mailboxes opened
     // through CUDA IPC, the device array of all of them, and the run counter that makes sequence words unique
     se3::DeviceBuf mailbox, mailbox_table;
+    se3::DeviceBuf knn_list, knn_count;  // compacted query list of a partial kNN / feature pass
     void* peer_ptr[se3::kMaxPeers] = {nullptr};
     bool peer_ready = false;
     unsigned long long peer_runs = 0;

@@ -175,6 +175,10 @@ struct FeatureArgs {
     double* knn_d2;   // optional [n*K]
     int K;            // list length = max(k_lrf, k_nrm, requested)
     int q_begin, q_end;  // only points whose ORIGINAL index lies in [q_begin, q_end) are processed (sharded source)
+    // partial range: the Morton positions of those points, compacted by launch_knn_features itself (scratch of n ints
+    // + 1 counter), so that the warps of a block all have work wherever the range lies in the Morton order
+    int* active_list;
+    int* active_count;
 };
 int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t st);
 int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, double* cov /*[6][n]*/, cudaStream_t st);

@@ -196,11 +196,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
     extern __shared__ __align__(16) unsigned char knn_smem[];  // dynamic: more than 48 KB from 12 warps per block on
     KnnScratch* scratch = reinterpret_cast<KnnScratch*>(knn_smem);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    // query = Morton position s.  Warps past the end redo the last query without writing, so the whole
-    // block reaches the __syncthreads() of the batched eigen-solves below.
-    const int s_raw = blockIdx.x * kKnnWarps + wib;
-    const bool in_range = s_raw < I.n;
-    const int s = in_range ? s_raw : I.n - 1;
+    // query = Morton position s: warp w takes position w, or entry w of the compacted list of a partial range.  Warps past
+    // the end redo the last query without writing, so the whole block reaches the __syncthreads() of the batched
+    // eigen-solves below.
+    const int w_raw = blockIdx.x * kKnnWarps + wib;
+    const int n_queries = fa.active_count ? *fa.active_count : I.n;
+    if (blockIdx.x * kKnnWarps >= n_queries) return;  // block-uniform
+    const bool in_range = w_raw < n_queries;
+    const int s = !in_range ? I.n - 1 : (fa.active_list ? fa.active_list[w_raw] : w_raw);
     KnnScratch& W = scratch[wib];
 
     const double qx = I.sx[s], qy = I.sy[s], qz = I.sz[s];
@@ -530,6 +533,24 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
     }
 }
 
+// Morton positions whose original index lies in [q_begin, q_end), compacted (order kept inside a warp, roughly kept
+// across warps: neighbouring queries stay neighbours, which is all the locality the search wants)
+__global__ void __launch_bounds__(256) knn_active_kernel(const int* __restrict__ perm, int n, int q_begin, int q_end,
+                                                          int* __restrict__ list, int* __restrict__ count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    bool on = false;
+    if (s < n) {
+        const int o = perm[s];
+        on = o >= q_begin && o < q_end;
+    }
+    const unsigned m = __ballot_sync(SE3_FULL, on);
+    if (m == 0u) return;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(SE3_FULL, base, __ffs(m) - 1);
+    if (on) list[base + __popc(m & ((1u << lane) - 1u))] = s;
+}
+
 __global__ void __launch_bounds__(256) cov_from_normals_kernel(const double* __restrict__ nrm, int n, double eps,
                                                                 double* __restrict__ cov) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -565,7 +586,16 @@ int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t
         SE3_CUDA(cudaFuncSetAttribute(knn_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    knn_features_kernel<<<blocks, kKnnWarps * 32, smem, st>>>(I, fa);
+    FeatureArgs args = fa;
+    const bool partial = fa.q_begin > 0 || fa.q_end < I.n;
+    if (partial && fa.active_list && fa.active_count) {
+        SE3_CUDA(cudaMemsetAsync(fa.active_count, 0, sizeof(int), st));
+        knn_active_kernel<<<(I.n + 255) / 256, 256, 0, st>>>(I.perm, I.n, fa.q_begin, fa.q_end, fa.active_list, fa.active_count);
+    } else {
+        args.active_list = nullptr;
+        args.active_count = nullptr;
+    }
+    knn_features_kernel<<<blocks, kKnnWarps * 32, smem, st>>>(I, args);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }

@@ -16,13 +16,16 @@ def shard_range(n, world, rank):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def dealt_order(n, world, block=4096):
+def dealt_order(n, world, block=32768):
     """Permutation that deals `n` points to `world` ranks in blocks of `block` consecutive points and lays every rank's
     share out contiguously: after `cloud[dealt_order(n, world)]` the contiguous range shard_range(n, world, r) of rank r
     holds the blocks r, r + world, r + 2 world, ... of the original order.  A scan is ordered by image row or by laser
     ring, so plain contiguous ranges give the ranks different parts of the scene and different search costs; dealing
     the blocks out balances them while se3icp_run_sharded still gets one contiguous range per rank.  (A point cloud is
-    an unordered set: the registration result does not depend on the order beyond summation order.)"""
+    an unordered set: the registration result does not depend on the order beyond summation order.)
+    Measured on the 10.1 M-point pair over 8 GPUs (profiles/sharded_blocks.py): contiguous ranges 257 ms (search time
+    per rank 152-185 ms), blocks of 4096 / 32768 / 262144 points 239 / 236 / 241 ms (larger blocks keep more of the
+    scan order's locality, smaller ones balance better)."""
     n, world, block = int(n), int(world), int(block)
     if world <= 1:
         return np.arange(n, dtype=np.int64)

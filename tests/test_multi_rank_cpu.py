@@ -77,6 +77,9 @@ def test_dealt_order_balances_contiguous_ranges(pkg):
         assert hist.min() > 0.7 * len(share) / 8 and hist.max() < 1.3 * len(share) / 8  # one 4096-point block is a quarter of a bin
         # and they come in runs of consecutive points (memory order inside a block is kept)
         assert np.mean(np.diff(share) == 1) > 0.99
+    # default block size: still a permutation with balanced shares
+    p = sh.dealt_order(10_000_000, 8)
+    assert np.array_equal(np.sort(p), np.arange(10_000_000))
 
 
 def test_world2_gloo(tmp_path):
