@@ -171,6 +171,12 @@ int fill_config(se3icp_ctx* c, const se3icp_params* p) {
     // Tracking the second-nearest distance costs ~2 % of a search (measured), so the filter is always armed;
     // the threshold remains as a tuning knob (||T_prev - T_total||_F of the last iteration).
     cfg.coherence_thr = 1e300;
+    // while the estimate still jumps, the remembered match is a poor starting point (tuning knob; exactness unaffected)
+    static const double reseed_thr = [] {
+        const char* e = getenv("SE3ICP_RESEED_THR");
+        return e && *e ? atof(e) : 0.05;
+    }();
+    cfg.reseed_thr = reseed_thr;
     cfg.mse = p->mse;
     cfg.mse_switch = p->mse_switch_error;
     cfg.alpha = p->alpha_rot;

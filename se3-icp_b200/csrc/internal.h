@@ -95,6 +95,7 @@ struct RunConfig {
     int coherence;       // SE(3) search may skip queries whose remembered match is provably still the nearest
     int coherence_xyz;   // same for the 3-D search of the ICP phase / run_icp
     double coherence_thr;  // ... once ||T_prev - T_total||_F of the last iteration is below this
+    double reseed_thr;     // unsettled queries also try a fresh Morton seed while that change is above this
     double mse;
     double mse_switch;
     double alpha;
@@ -122,7 +123,7 @@ struct TargetView {
     // SE(3) search structure: rows in 6-D Morton order (se3_index.cu); level layout shared with idx
     const float4* rows32; // [3][n]  (alpha R | tscale p) as floats
     const double* rows64; // [12][n]
-    const float2* box12;  // [12][total_nodes] (lo, hi) per dimension, rounded outwards
+    const float2* box12;  // (lo, hi) per dimension, rounded outwards; two dimensions per 16-byte word: box12_slot()
     const int* perm12;    // 6-D position -> original index
     const int* inv12;     // original index -> 6-D position
     const uint64_t* keys12;
@@ -132,6 +133,12 @@ struct TargetView {
 
 constexpr int kTcountWords = 4 + 64;
 constexpr int kTrimHistBins = 65536;  // histogram of the top 16 bits of the distance keys of one iteration
+
+// 12-D boxes: dimensions 2 j and 2 j + 1 of a node share one float4 (lo, hi, lo, hi) in plane j of 6, so that a node test
+// is six 16-byte loads.  Index of the float2 holding dimension k of `node`:
+__host__ __device__ inline size_t box12_slot(int k, int node, size_t total_nodes) {
+    return ((size_t)(k >> 1) * total_nodes + (size_t)node) * 2 + (size_t)(k & 1);
+}
 
 struct CorrBuffers {
     double* d2_nd;   // optional [N] squared distance in the search space (12-D or 3-D), stage API

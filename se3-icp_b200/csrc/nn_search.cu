@@ -260,13 +260,42 @@ int launch_nn_se3_repair(const SourceView& S, const TargetView& T, const RunConf
 }
 
 // ------------------------------------------------------------------------------------------------
+// row position of the target SE(3) row whose 6-D Morton key is closest to the query's (binary search over the sorted keys)
+__device__ __forceinline__ int seed_position_se3(const TargetView& T, const RunConfig& cfg, const double q[12]) {
+    double Ru[9];
+    const double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
+    const double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
+    const uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
+    int lo = 0, hi = T.n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo >= T.n ? T.n - 1 : lo;
+}
+
+__device__ __forceinline__ int seed_position_xyz(const CloudIndex& I, double qx, double qy, double qz) {
+    const uint64_t key = morton63(qx, qy, qz, I.bbox);
+    int lo = 0, hi = I.n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (I.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo >= I.n ? I.n - 1 : lo;
+}
+
 // Per-query preparation of a correspondence pass, one THREAD per query (coalesced plane loads), run before both searches:
-//  * seeding — a query without a remembered match (first iteration of a run) gets the target row whose Morton key is
-//    closest to its own as a stand-in "previous match": key construction and the 17-step binary search run once per
-//    thread here instead of 32-fold redundantly in every lane of the warp-per-query search kernel, which then has a
-//    single, warm-started code path;
 //  * coherence filter — settles every query whose remembered match is provably still its unique nearest neighbour and
-//    appends the others to the work list the search kernels consume.
+//    appends the others to the work list the search kernels consume;
+//  * seeding — an unsettled query gets a starting point for its search from the Morton order of the search structure
+//    (key construction + a 17-step binary search, once per thread here instead of 32-fold redundantly in every lane of
+//    the warp-per-query search kernel, which is left with a single, warm-started code path): always when it has no
+//    remembered match (first pass of a run) and on the first ICP-phase pass (the remembered match is the 12-D one,
+//    possibly far in position); and, while the estimate still moves a lot (||T_prev - T||_F > cfg.reseed_thr), whenever
+//    the seed is closer than the remembered match — measured: with the remembered match alone the second pass of a
+//    KITTI-size pair cost more than the cold first one.  The search is exact from any starting point.
 __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                          IterState* __restrict__ state, CorrBuffers cb) {
     if (state->done) return;
@@ -278,85 +307,66 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
     const int i = S.order ? S.order[t] : t;
     const double* Tm = state->T_total;
     const size_t n = (size_t)S.n, m = (size_t)T.n;
-    bool settled = false;
     int prev = cb.idx[i];
-    // first ICP-phase pass after the SE(3) phase: the remembered match is the 12-D one, whose position may be far from
-    // the query; the better of it and a fresh Morton seed becomes the starting point
-    const bool reseed = !se3 && cfg.has_se3 && state->iter == state->switch_iter;
-    if (prev < 0 || prev >= T.n || reseed) {  // seed from the Morton order of the search structure
-        int lo = 0, hi = T.n;
-        if (se3) {
-            double q[12];
-            make_query(S, cfg, Tm, i, q);
-            double Ru[9];
-            const double inv_a = cfg.alpha != 0.0 ? 1.0 / cfg.alpha : 0.0;
-#pragma unroll
-            for (int k = 0; k < 9; k++) Ru[k] = q[k] * inv_a;
-            const double inv_t = T.tscale != 0.0 ? 1.0 / T.tscale : 0.0;
-            const uint64_t key = se3_key(Ru, q[9] * inv_t, q[10] * inv_t, q[11] * inv_t, T.idx.bbox);
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (T.keys12[mid] < key) lo = mid + 1; else hi = mid;
-            }
-            if (lo >= T.n) lo = T.n - 1;
-            prev = T.perm12[lo];
-        } else {
-            const double px = S.x[i], py = S.y[i], pz = S.z[i];
-            const double qx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3], qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7],
-                         qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
-            const uint64_t key = morton63(qx, qy, qz, T.idx.bbox);
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (T.idx.keys[mid] < key) lo = mid + 1; else hi = mid;
-            }
-            if (lo >= T.n) lo = T.n - 1;
-            const int seed = T.idx.perm[lo];
-            if (prev >= 0 && prev < T.n &&
-                sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]) <=
-                    sqdist3(qx, qy, qz, T.idx.x[seed], T.idx.y[seed], T.idx.z[seed])) {
-                // the 12-D match is at least as close: keep it
-            } else {
-                prev = seed;
-            }
-        }
-        cb.idx[i] = prev;  // (a seed carries no certificate: ref_d2nd[i] is still "not known" from the set-up)
-    }
-    if (!enabled) return;
-    const double dref = cb.ref_d2nd[i];
+    const bool have_prev = prev >= 0 && prev < T.n;
+    const bool first_icp_pass = !se3 && cfg.has_se3 && state->iter == state->switch_iter;
+    const bool want_seed = !have_prev || first_icp_pass || state->T_change > cfg.reseed_thr;
     // the first ICP-phase iteration still sees the 12-D references of the SE(3) phase: ignore them once
-    const bool refs_match_space = se3 || !(cfg.has_se3 && state->iter == state->switch_iter);
-    if (prev >= 0 && prev < T.n && dref >= 0.0 && refs_match_space) {
-        if (se3) {
-            double q[12];
-            make_query(S, cfg, Tm, i, q);
+    const bool try_settle = enabled && have_prev && !first_icp_pass && cb.ref_d2nd[i] >= 0.0;
+    if (!try_settle && !want_seed) {
+        if (enabled) cb.work[atomicAdd(&state->work_count, 1)] = i;
+        return;
+    }
+    bool settled = false;
+    if (se3) {
+        double q[12];
+        make_query(S, cfg, Tm, i, q);
+        double d_prev = -1.0;
+        if (try_settle) {
             double dl = 0.0;
 #pragma unroll
             for (int k = 0; k < 12; k++) {
                 double df = q[k] - cb.ref_q[k * n + i];
                 dl += df * df;
             }
-            int j = T.inv12[prev];
-            double d1sq = exact_d2_12(q, T.rows64, m, j);
-            if ((sqrt(d1sq) + sqrt(dl)) * (1.0 + 1e-12) + 1e-300 < dref) {
-                write_se3_match(T, cfg, cb, i, q, j, d1sq);
-                settled = true;
-            }
-        } else {
-            const double px = S.x[i], py = S.y[i], pz = S.z[i];
-            const double qx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3];
-            const double qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
-            const double qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
-            double ex = qx - cb.ref_q[i], ey = qy - cb.ref_q[n + i], ez = qz - cb.ref_q[2 * n + i];
-            double d1sq = sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]);
-            double d1 = sqrt(d1sq);
-            if ((d1 + sqrt(ex * ex + ey * ey + ez * ez)) * (1.0 + 1e-12) + 1e-300 < dref) {
-                store_distance(cfg, cb, i, d1);
-                if (cb.d2_nd) cb.d2_nd[i] = d1sq;
+            const int j = T.inv12[prev];
+            d_prev = exact_d2_12(q, T.rows64, m, j);
+            if ((sqrt(d_prev) + sqrt(dl)) * (1.0 + 1e-12) + 1e-300 < cb.ref_d2nd[i]) {
+                write_se3_match(T, cfg, cb, i, q, j, d_prev);
                 settled = true;
             }
         }
+        if (!settled && want_seed) {
+            const int js = seed_position_se3(T, cfg, q);
+            if (have_prev) {
+                if (d_prev < 0.0) d_prev = exact_d2_12(q, T.rows64, m, T.inv12[prev]);
+                if (exact_d2_12(q, T.rows64, m, js) < d_prev) cb.idx[i] = T.perm12[js];
+            } else {
+                cb.idx[i] = T.perm12[js];
+            }
+        }
+    } else {
+        const double px = S.x[i], py = S.y[i], pz = S.z[i];
+        const double qx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3];
+        const double qy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
+        const double qz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
+        double d_prev = -1.0;
+        if (have_prev) d_prev = sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]);
+        if (try_settle) {
+            const double ex = qx - cb.ref_q[i], ey = qy - cb.ref_q[n + i], ez = qz - cb.ref_q[2 * n + i];
+            const double d1 = sqrt(d_prev);
+            if ((d1 + sqrt(ex * ex + ey * ey + ez * ez)) * (1.0 + 1e-12) + 1e-300 < cb.ref_d2nd[i]) {
+                store_distance(cfg, cb, i, d1);
+                if (cb.d2_nd) cb.d2_nd[i] = d_prev;
+                settled = true;
+            }
+        }
+        if (!settled && want_seed) {
+            const int seed = T.idx.perm[seed_position_xyz(T.idx, qx, qy, qz)];
+            if (!have_prev || sqdist3(qx, qy, qz, T.idx.x[seed], T.idx.y[seed], T.idx.z[seed]) < d_prev) cb.idx[i] = seed;
+        }
     }
-    if (!settled) cb.work[atomicAdd(&state->work_count, 1)] = i;
+    if (enabled && !settled) cb.work[atomicAdd(&state->work_count, 1)] = i;
 }
 
 int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
@@ -409,18 +419,25 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
         qamax = fmaxf(qamax, fabsf(qf[k]));
     }
     const float qeps = qamax * 1.1920929e-07f;  // 2^-23 |q|max: twice the worst rounding of any coordinate
-    // rigorous FP32 lower bound: every operation rounds toward the smaller result
+    // Rigorous FP32 lower bound of the squared distance from the query to a node's box.  Per dimension the gap
+    // d_k = max(0, lo_k - qf_k, qf_k - hi_k) is rounded down; the true gap (for the FP64 query) is at least
+    // (d_k - qeps)+, and sum (d_k - qeps)+^2 >= S - 2 qeps sum d_k >= S - 2 sqrt(12) qeps sqrt(S) with S = sum d_k^2
+    // (Cauchy-Schwarz), so the rounding of the query costs one correction per node instead of two operations per
+    // dimension.  S is accumulated with round-down FMAs; S - c sqrt(S) grows with S wherever it is positive, so the
+    // smaller computed S keeps the bound valid.  Two dimensions per 16-byte load (box12_slot).
+    const float qcorr = __fmul_ru(7.f, qeps);  // > 2 sqrt(12) qeps
     auto lb_fn = [&](int node) -> double {
-        const float2* b = T.box12 + node;
+        const float4* b = reinterpret_cast<const float4*>(T.box12) + node;
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-            const float2 lh = b[(size_t)k * tn];
-            float d = fmaxf(__fsub_rd(lh.x, qf[k]), __fsub_rd(qf[k], lh.y));
-            d = fmaxf(0.f, __fsub_rd(d, qeps));
-            acc = __fmaf_rd(d, d, acc);  // exact d*d + acc rounded down: still a lower bound, one instruction
+        for (int kk = 0; kk < 6; kk++) {
+            const float4 v = b[(size_t)kk * tn];
+            float d0 = fmaxf(fmaxf(__fsub_rd(v.x, qf[2 * kk]), __fsub_rd(qf[2 * kk], v.y)), 0.f);
+            float d1 = fmaxf(fmaxf(__fsub_rd(v.z, qf[2 * kk + 1]), __fsub_rd(qf[2 * kk + 1], v.w)), 0.f);
+            acc = __fmaf_rd(d0, d0, acc);  // exact d*d + acc rounded down: still a lower bound, one instruction
+            acc = __fmaf_rd(d1, d1, acc);
         }
-        return (double)acc;
+        return (double)fmaxf(0.f, __fsub_rd(acc, __fmul_ru(qcorr, __fsqrt_ru(acc))));
     };
 
     // ---- temporal coherence (DESIGN.md "coherence filter") -----------------------------------------------

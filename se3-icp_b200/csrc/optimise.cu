@@ -751,9 +751,22 @@ __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState*
     __shared__ double wsum[8][kReducePartials];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     {   // fixed-order sum of the per-block records: warp w takes records w, w+8, ...; then the 8 warp sums in order
+        // (eight independent L2 loads in flight, added in the fixed order b = w, w + 8, ...: one dependent load per
+        // addition made this chain 13 us long)
         double s = 0.0;
-        if (lane < kAcc)
-            for (int b = w; b < n_records; b += 8) s += __ldcg(&partials[b * kReducePartials + lane]);
+        if (lane < kAcc) {
+            for (int b0 = w; b0 < n_records; b0 += 64) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int b = b0 + 8 * u;
+                    v[u] = b < n_records ? __ldcg(&partials[b * kReducePartials + lane]) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (b0 + 8 * u < n_records) s += v[u];
+            }
+        }
         wsum[w][lane] = s;
     }
     if (hist)

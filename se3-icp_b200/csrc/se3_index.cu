@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) box12_leaf_kernel(const double* __restric
         if (p < n) lo = hi = rows64[k * nn + p];
         lo = warp_min(lo);
         hi = warp_max(hi);
-        if (lane == 0) box12[(size_t)k * tn + warp] = make_float2(__double2float_rd(lo), __double2float_ru(hi));
+        if (lane == 0) box12[box12_slot(k, warp, tn)] = make_float2(__double2float_rd(lo), __double2float_ru(hi));
     }
 }
 
@@ -86,13 +86,13 @@ __global__ void __launch_bounds__(256) box12_upper_kernel(int child_off, int chi
     for (int k = 0; k < 12; k++) {
         float lo = 3.0e38f, hi = -3.0e38f;
         if (c < child_cnt) {
-            const float2 lh = box12[(size_t)k * tn + child_off + c];
+            const float2 lh = box12[box12_slot(k, child_off + c, tn)];
             lo = lh.x;
             hi = lh.y;
         }
         lo = warp_minf(lo);
         hi = warp_maxf(hi);
-        if (lane == 0) box12[(size_t)k * tn + node_off + warp] = make_float2(lo, hi);
+        if (lane == 0) box12[box12_slot(k, node_off + warp, tn)] = make_float2(lo, hi);
     }
 }
 

@@ -11,16 +11,33 @@ namespace se3 {
 
 constexpr int kStackEntries = 192;  // >= 31 * levels + 1 for up to 6 levels (n <= 32^6)
 
-__device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node, double qx, double qy, double qz) {
+// FP32 image of a 3-D query for the box tests: the coordinates rounded to float and a correction term covering that
+// rounding (see box_lower_bound)
+struct BoxQuery {
+    float x, y, z, corr;
+};
+
+__device__ __forceinline__ BoxQuery make_box_query(double qx, double qy, double qz) {
+    BoxQuery q;
+    q.x = (float)qx, q.y = (float)qy, q.z = (float)qz;
+    // |q_k - float(q_k)| <= 2^-24 |q_k| <= eps := 2^-23 max|q|; corr > 2 sqrt(3) eps
+    q.corr = __fmul_ru(3.5f * 1.1920929e-07f, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z)));
+    return q;
+}
+
+// Rigorous FP32 lower bound of the squared distance from the (FP64) query to a node's box, the boxes being rounded
+// outwards: per axis the gap d_k = max(0, lo_k - qf_k, qf_k - hi_k) is rounded down, the true gap is at least
+// (d_k - eps)+, and sum (d_k - eps)+^2 >= S - 2 eps sum d_k >= S - 2 sqrt(3) eps sqrt(S) with S = sum d_k^2.
+// S - c sqrt(S) grows with S wherever it is positive, so accumulating S with round-down FMAs keeps the bound valid.
+__device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node, const BoxQuery& q) {
     const float2* b = I.box + node;
-    size_t tn = (size_t)I.total_nodes;
+    const size_t tn = (size_t)I.total_nodes;
     const float2 bx = b[0], by = b[tn], bz = b[2 * tn];
-    double lox = bx.x, loy = by.x, loz = bz.x;
-    double hix = bx.y, hiy = by.y, hiz = bz.y;
-    double dx = fmax(0.0, fmax(lox - qx, qx - hix));
-    double dy = fmax(0.0, fmax(loy - qy, qy - hiy));
-    double dz = fmax(0.0, fmax(loz - qz, qz - hiz));
-    return dx * dx + dy * dy + dz * dz;
+    const float dx = fmaxf(fmaxf(__fsub_rd(bx.x, q.x), __fsub_rd(q.x, bx.y)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(by.x, q.y), __fsub_rd(q.y, by.y)), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(bz.x, q.z), __fsub_rd(q.z, bz.y)), 0.f);
+    const float s = __fmaf_rd(dz, dz, __fmaf_rd(dy, dy, __fmul_rd(dx, dx)));
+    return (double)fmaxf(0.f, __fsub_rd(s, __fmul_ru(q.corr, __fsqrt_ru(s))));
 }
 
 // `tau` is read on every test, so the leaf functor may shrink it while the traversal runs.
@@ -80,7 +97,8 @@ __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn
 template <bool kWideStart, class LeafFn>
 __device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, double qy, double qz, const double& tau,
                                                int2* stack, int lane, LeafFn&& leaf_fn) {
-    traverse_nodes<kWideStart>(I, [&](int node) { return box_lower_bound(I, node, qx, qy, qz); }, tau, stack, lane, leaf_fn);
+    const BoxQuery bq = make_box_query(qx, qy, qz);
+    traverse_nodes<kWideStart>(I, [&](int node) { return box_lower_bound(I, node, bq); }, tau, stack, lane, leaf_fn);
 }
 
 }  // namespace se3
