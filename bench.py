@@ -256,6 +256,23 @@ def configs_block(capi, orc, device):
                         "rot_vs_oracle_rad": W.rotation_error(T, To),
                         "transl_vs_oracle_rel_extent": float(np.abs(T[:3, 3] - To[:3, 3]).max() / extent),
                         "rot_vs_gt_rad": W.rotation_error(T, T_gt), "oracle_cpu_ms": cpu_ms})
+    # configs[3] as the reference runs it (benchmark_lounge.cpp:154-186): a sequence of independent frame pairs,
+    # se3_gicp_with_cf; here 8 pairs (4 synthetic scenes x 2) through se3icp_run_batch on 4 contexts, host buffers in
+    frames = [W.rgbd_pair(seed=k) for k in range(4)]
+    batch = [(frames[k % 4][0], frames[k % 4][1]) for k in range(8)]
+    pl = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP_CF, **W.LOUNGE_PARAMS)
+    ctxs = [capi.Context(device) for _ in range(4)]
+    capi.run_batch(ctxs, batch, pl)
+    t0 = time.perf_counter()
+    T, st = capi.run_batch(ctxs, batch, pl)
+    dt = time.perf_counter() - t0
+    for c in ctxs:
+        c.close()
+    out.append({"config": "configs[3] lounge-like sequence, se3_gicp_with_cf: 8 independent frame pairs, 4 contexts, host buffers",
+                "points": [int(np.mean([len(f[0]) for f in frames])), int(np.mean([len(f[1]) for f in frames]))],
+                "registrations_per_s": len(batch) / dt, "wall_ms": 1e3 * dt,
+                "iterations": [int(s.num_iterations) for s in st[:4]],
+                "max_rot_err_vs_gt_rad": max(W.rotation_error(T[k], frames[k % 4][2]) for k in range(8))})
     return out
 
 

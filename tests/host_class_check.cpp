@@ -1,0 +1,67 @@
+// host_class_check.cpp — checks of the drop-in class that no reference driver exercises (built by
+// se3-icp_b200/host/Makefile into se3-icp_b200/bin/host_class_check, run by tests/test_host_driver.py on the GPU):
+//   * the class is copyable like the reference's: a copy carries the configuration and the clouds and registers on a
+//     GPU context of its own;
+//   * set_mirror_state(true) reproduces the member state the reference leaves behind after run_se3_icp:
+//     source_ / target_ centred and scaled (.cpp:568-582), source_moving_ at the estimate (.cpp:706), correspondences
+//     and SE(3) clouds filled (hpp:59-60,74-75).
+// usage: host_class_check source.ply target.ply      prints HOST_CLASS_CHECK OK
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+
+#include "iterative_SE3_registration.hpp"
+
+static int fail(const char* what) {
+    std::printf("HOST_CLASS_CHECK FAILED: %s\n", what);
+    return 1;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) return fail("usage: host_class_check source.ply target.ply");
+    IterativeSE3Registration a;
+    a.setSourceCloud(std::string(argv[1]));
+    a.setTargetCloud(std::string(argv[2]));
+    a.max_num_se3_iterations_ = 10;
+    a.mse_switch_error_ = 5e-5;
+    a.number_of_nn_for_LRF_ = 90;
+    a.set_mirror_state(true);
+
+    IterativeSE3Registration b(a);  // copy before the run: same fields, same clouds, its own context
+    if (b.number_of_nn_for_LRF_ != 90 || b.source_.points_.size() != a.source_.points_.size()) return fail("copy lost state");
+    const open3d::geometry::PointCloud raw_source = a.source_;
+
+    a.run_se3_icp("pt2pl");
+    b.run_se3_icp("pt2pl");
+    if ((a.current_estimated_T_ - b.current_estimated_T_).norm() != 0.0) return fail("the copy registered differently");
+    if (a.num_iterations_ != b.num_iterations_) return fail("the copy iterated differently");
+
+    IterativeSE3Registration c;
+    c = a;  // assignment after the run carries the results as well
+    if ((c.current_estimated_T_ - a.current_estimated_T_).norm() != 0.0 || c.num_iterations_ != a.num_iterations_)
+        return fail("assignment lost the results");
+
+    // mirror state
+    const size_t n = raw_source.points_.size();
+    if (a.source_.points_.size() != n || a.source_moving_.points_.size() != n) return fail("cloud sizes changed");
+    if (a.source_.GetCenter().norm() > 1e-9) return fail("source_ not centred");
+    if (a.target_.GetCenter().norm() > 1e-9) return fail("target_ not centred");
+    const double r = std::max(largestDistanceFromGivenPoint(Eigen::Vector3d(0, 0, 0), a.source_),
+                              largestDistanceFromGivenPoint(Eigen::Vector3d(0, 0, 0), a.target_));
+    if (std::fabs(r - 3.0) > 1e-9) return fail("clouds not scaled to scale_preprocessing");
+    if (a.current_correspondences_set.correspondences_vec.size() != n || a.current_correspondences_set_pcl->size() != n)
+        return fail("correspondences not mirrored");
+    if (a.source_se3_cloud_.size() != n || a.target_se3_cloud_.size() != a.target_.points_.size()) return fail("SE(3) clouds not mirrored");
+    // source_moving_ sits on its correspondences: the fixture is an exact copy, so matched points coincide
+    double worst = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const int j = a.current_correspondences_set.correspondences_vec[i](1);
+        worst = std::max(worst, (a.source_moving_.points_[i] - a.target_.points_[j]).norm());
+    }
+    if (worst > 1e-6) return fail("source_moving_ is not at the estimate");
+    // and the translation column of a mirrored SE(3) element is beta * the moved point (.cpp:605-607,713-716)
+    Eigen::Vector3d t0 = a.source_se3_cloud_[0].block<3, 1>(0, 3);
+    if ((t0 - a.source_moving_.points_[0] * a.beta_transl).norm() > 1e-9) return fail("source_se3_cloud_ inconsistent with source_moving_");
+    std::printf("HOST_CLASS_CHECK OK (%zu points, %d iterations, worst matched distance %.2e)\n", n, a.num_iterations_, worst);
+    return 0;
+}

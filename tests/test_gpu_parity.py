@@ -214,6 +214,35 @@ def test_trim_matches_oracle(ctx, orc, overlap, keep_largest):
             np.testing.assert_array_equal(np.sort(d[gkeep]), np.sort(d[okeep]))
 
 
+def test_trim_multipass_kernels_agree():
+    """The sharded pair selects the trimmed threshold with four all-reducible 8-bit histogram passes and a keep mask; one
+    GPU uses the single-pass selection.  The same entry point runs the former with SE3ICP_TRIM_MULTIPASS=1 (read once
+    per process, hence the subprocess): both must return the oracle's kept set."""
+    import subprocess
+    import sys
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as g
+capi, orc = g.load_package().capi, g.load_oracle()
+rng = np.random.default_rng(5)
+with capi.Context(0) as ctx:
+    for n in (1, 7, 4167, 100000):
+        d = rng.gamma(2.0, 0.01, n).astype(np.float32)
+        d[::17] = d[0]  # ties
+        for ov in (0.99, 0.7, 0.5, 0.01):
+            for kl in (False, True):
+                gk, gkeep = ctx.trim(d, ov, kl)
+                ok, okeep = orc.trim(d, ov, kl)
+                assert gk == ok == int(gkeep.sum()), (n, ov, kl)
+                assert np.array_equal(np.sort(d[gkeep]), np.sort(d[okeep])), (n, ov, kl)
+print("TRIM_MULTIPASS_OK")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, SE3ICP_TRIM_MULTIPASS="1"))
+    assert "TRIM_MULTIPASS_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
 def test_trim_ties(ctx, orc):
     d = np.zeros(1000, np.float32)           # converged exact copy: every distance is 0
     d[::3] = 0.5
@@ -370,6 +399,33 @@ def test_invalid_variant_behaviour(pkg, c1, capsys):
     np.testing.assert_allclose(T[:3, :3], np.eye(3))
     np.testing.assert_allclose(T[:3, 3], tgt.mean(0) - src.mean(0))
     assert "Invalid variant name" in capsys.readouterr().err
+
+
+def test_pending_run_and_stage_calls_guard_the_context(capi, c1):
+    """While an asynchronous run is pending the context refuses everything that would touch its buffers, and a
+    stage-level call leaves it without clouds (SE3ICP_ERR_STATE instead of a run on half-overwritten data)."""
+    src, tgt, _ = c1
+    p = capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, **RRM)
+    with capi.Context(0) as c:
+        c.set_cloud(capi.SOURCE, src)
+        c.set_cloud(capi.TARGET, tgt)
+        T0, s0 = c.run(p)
+        c.run_async(p)
+        for call in (lambda: c.set_cloud(capi.SOURCE, src), lambda: c.run_async(p), lambda: c.swap_clouds(),
+                     lambda: c.knn(src, 5), lambda: c.trim(np.ones(10, np.float32), 0.5)):
+            with pytest.raises(capi.Se3IcpError) as e:
+                call()
+            assert e.value.code == 6  # SE3ICP_ERR_STATE
+        T1, s1 = c.run_finish()
+        np.testing.assert_array_equal(T0, T1)
+        c.knn(src, 5)  # a stage call borrows the cloud slots ...
+        with pytest.raises(capi.Se3IcpError) as e:
+            c.run(p)   # ... so the context holds no clouds afterwards
+        assert e.value.code == 6
+        c.set_cloud(capi.SOURCE, src)
+        c.set_cloud(capi.TARGET, tgt)
+        T2, _ = c.run(p)
+        np.testing.assert_array_equal(T0, T2)
 
 
 def test_set_cloud_appends(pkg, c1):

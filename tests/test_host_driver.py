@@ -34,6 +34,19 @@ def test_driver_usage_and_bad_name(tmp_path):
 
 
 @pytest.mark.gpu
+def test_host_class_copy_and_mirror_state(tmp_path):
+    """tests/host_class_check.cpp: the C++ class is copyable and, with set_mirror_state, leaves the reference's
+    post-run member state (normalised clouds, moved source, correspondences, SE(3) clouds)"""
+    exe = os.path.join(BIN_DIR, "host_class_check")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    src, tgt, _ = W.load_c1()
+    W.write_ply(str(tmp_path / "s.ply"), src)
+    W.write_ply(str(tmp_path / "t.ply"), tgt)
+    r = subprocess.run([exe, str(tmp_path / "s.ply"), str(tmp_path / "t.ply")], capture_output=True, text=True, timeout=300)
+    assert "HOST_CLASS_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("method", ["se3_pt2pl", "se3_pt2pt", "se3_gicp", "pt2pt", "pt2pl", "gicp"])
 def test_driver_registers_fixture(tmp_path, method):
     """README command: ./run_registration_method se3_pt2pl source.ply target.ply -> ground truth"""
