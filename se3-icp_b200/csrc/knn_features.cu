@@ -13,8 +13,9 @@
 
 namespace se3 {
 
-constexpr int kKnnWarps = 12;  // measured on B200: 8/12/16/24 warps per block -> 1.42/1.28/1.56/1.31 ms per 119 k-point cloud
-                               // (the block shares one batch of 3x3 eigen-solves; 12 x 2 blocks keeps 24 warps per SM)
+constexpr int kKnnWarps = 16;  // 16 warps x 2 blocks per SM at 64 registers: 1.02 ms per 119 k-point cloud (12 x 2 at 80 registers 1.10, 32 x 1 1.05,
+                               // 8 x 4 1.13, 24 x 1 at 80 registers 1.11): neighbouring queries share L1 lines, and 32 warps per SM hide the
+                               // latency of the serial selection loops better than 24 do, spills included
 constexpr int kPool = 256;  // unsorted candidate pool per warp
 
 struct KnnScratch {

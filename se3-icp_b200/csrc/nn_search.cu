@@ -379,7 +379,9 @@ int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& 
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int kTreeWarps = 4;  // 8 / 4 / 2 / 1 warps per block measured 7.51 / 7.36 / 7.40 / 7.65 ms per KITTI-size pair
+constexpr int kTreeWarps = 4;  // round 2, SE(3)-phase search of a KITTI-size pair: 4 warps x 10 blocks per SM (48 registers) 2.06 ms,
+                               // 4 x 8 (64 registers) 2.11, 2 x 16 2.08, 8 x 4 2.22, 16 x 2 2.40: queries differ in length, so small blocks
+                               // (a block holds its slot until its slowest warp is done) and more resident warps win here
 
 __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetView& T, const RunConfig& cfg,
                                               IterState* __restrict__ state, CorrBuffers& cb,
@@ -641,7 +643,7 @@ __device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& 
 // One kernel for the correspondence stage of an iteration: the phase flag lives on the device, so the kernel
 // picks the 12-D or the 3-D search itself (which = 0), instead of launching both and letting one early-out.
 // which = 1 / 2 restricts it to the SE(3) / XYZ search (stage-level entry points, timing hook).
-__global__ void __launch_bounds__(kTreeWarps * 32, 8) nn_search_kernel(SourceView S, TargetView T, RunConfig cfg,
+__global__ void __launch_bounds__(kTreeWarps * 32, 10) nn_search_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                                         IterState* __restrict__ state, CorrBuffers cb,
                                                                         int which) {
     if (state->done) return;
