@@ -82,7 +82,11 @@ SourceView se3icp_ctx::source_view() const {
     S.n = (int)n[0];
     S.begin = sharded ? shard_begin : 0;
     S.end = sharded ? shard_end : (int)n[0];
-    S.order = (!sharded && src_index_built) ? index[0].perm.as<int>() : nullptr;
+    static const bool use_order = [] {
+        const char* e = getenv("SE3ICP_SRC_ORDER");
+        return !(e && atoi(e) == 0);
+    }();
+    S.order = (use_order && !sharded && src_index_built) ? index[0].perm.as<int>() : nullptr;
     S.x = index[0].x.as<double>();
     S.y = index[0].y.as<double>();
     S.z = index[0].z.as<double>();

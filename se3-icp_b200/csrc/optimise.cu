@@ -676,7 +676,7 @@ int launch_sum_partials(const double* partials, double* total, cudaStream_t st) 
     return 0;
 }
 
-// Executed by one whole block of 256 threads: the stand-alone kernel below (sharded pair, stage API) or the last block
+// Executed by one whole block (128 or 256 threads): the stand-alone kernel below (sharded pair, stage API) or the last block
 // of reduce_kernel to finish (single-GPU loop).  cond_handle != 0: the caller is the last node of the captured loop
 // body and tells the WHILE node whether to run it again.
 constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
@@ -749,22 +749,22 @@ __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState*
     IterState* st = &s_state;
     __shared__ double tot[kReducePartials];
     __shared__ double wsum[8][kReducePartials];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    {   // fixed-order sum of the per-block records: warp w takes records w, w+8, ...; then the 8 warp sums in order
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;  // 4 or 8 warps
+    {   // fixed-order sum of the per-block records: warp w takes records w, w + nw, ...; then the warp sums in order
         // (eight independent L2 loads in flight, added in the fixed order b = w, w + 8, ...: one dependent load per
         // addition made this chain 13 us long)
         double s = 0.0;
         if (lane < kAcc) {
-            for (int b0 = w; b0 < n_records; b0 += 64) {
+            for (int b0 = w; b0 < n_records; b0 += 8 * nw) {
                 double v[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    const int b = b0 + 8 * u;
+                    const int b = b0 + nw * u;
                     v[u] = b < n_records ? __ldcg(&partials[b * kReducePartials + lane]) : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (b0 + 8 * u < n_records) s += v[u];
+                    if (b0 + nw * u < n_records) s += v[u];
             }
         }
         wsum[w][lane] = s;
@@ -774,8 +774,7 @@ __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState*
     __syncthreads();
     if (threadIdx.x < kAcc) {
         double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += wsum[k][threadIdx.x];
+        for (int k = 0; k < nw; k++) s += wsum[k][threadIdx.x];
         tot[threadIdx.x] = s;
     }
     __syncthreads();
@@ -831,21 +830,27 @@ __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState*
     st->mse_prev = st->mse_cur;
     st->mse_cur = mean;
     st->mse_rel = fabs(st->mse_cur - st->mse_prev);
-    double Tn[16];
+    double To[16], Tn[16];  // registers: this thread is a chain of dependent operations, keep shared memory out of it
+#pragma unroll
+    for (int k = 0; k < 16; k++) To[k] = st->T_total[k];
+#pragma unroll
     for (int r = 0; r < 4; r++)
+#pragma unroll
         for (int c = 0; c < 4; c++) {
             double s = 0.0;
-            for (int k = 0; k < 4; k++) s += Ti[4 * r + k] * st->T_total[4 * k + c];
+#pragma unroll
+            for (int k = 0; k < 4; k++) s += Ti[4 * r + k] * To[4 * k + c];
             Tn[4 * r + c] = s;
         }
     double ch = 0.0;
+#pragma unroll
     for (int k = 0; k < 16; k++) {
-        double df = st->T_total[k] - Tn[k];
+        double df = To[k] - Tn[k];
         ch += df * df;
-        st->T_prev[k] = st->T_total[k];
+        st->T_prev[k] = To[k];
         st->T_i[k] = Ti[k];
+        st->T_total[k] = Tn[k];
     }
-    for (int k = 0; k < 16; k++) st->T_total[k] = Tn[k];
     st->T_change = sqrt(ch);
     if (cfg.record_history && history && st->hist_count < cfg.max_history) {
         for (int k = 0; k < 16; k++) history[16 * (size_t)st->hist_count + k] = Ti[k];
@@ -900,15 +905,18 @@ __global__ void __launch_bounds__(256) solve_update_kernel(RunConfig cfg, IterSt
 // fuse.enabled: the block that finishes last also sums the per-block records (fixed order, so the result does not depend
 // on which block that is), solves, updates the estimate and decides whether the loop goes on — an iteration then ends
 // with this kernel.
-__global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T, RunConfig cfg, IterState* __restrict__ state,
-                                                      CorrBuffers cb, double* __restrict__ partials, SolveFusion fuse) {
+constexpr int kReduceThreads = 128;  // 168 registers per thread: three 128-thread blocks fit an SM, so the 296 blocks run in one
+                                     // wave (256-thread blocks: one per SM, two waves)
+__global__ void __launch_bounds__(kReduceThreads) reduce_kernel(SourceView S, TargetView T, RunConfig cfg,
+                                                                 IterState* __restrict__ state, CorrBuffers cb,
+                                                                 double* __restrict__ partials, SolveFusion fuse) {
     if (state->done) {
         if (fuse.enabled && fuse.cond_handle && blockIdx.x == 0 && threadIdx.x == 0)
             cudaGraphSetConditional((cudaGraphConditionalHandle)fuse.cond_handle, 0u);
         return;
     }
     __shared__ double Tm[16];
-    __shared__ double sm[8][kAcc];
+    __shared__ double sm[kReduceThreads / 32][kAcc];
     __shared__ int s_last;
     if (threadIdx.x < 16) Tm[threadIdx.x] = state->T_total[threadIdx.x];
     if (blockIdx.x == 0 && threadIdx.x == 0) stamp_correspondence_end(cfg, state);
@@ -1037,7 +1045,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
     __syncthreads();
     if (threadIdx.x < kAcc) {
         double s = 0.0;
-        for (int k = 0; k < 8; k++) s += sm[k][threadIdx.x];
+        for (int k = 0; k < kReduceThreads / 32; k++) s += sm[k][threadIdx.x];
         partials[blockIdx.x * kReducePartials + threadIdx.x] = s;
     }
     if (!fuse.enabled) return;
@@ -1054,7 +1062,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(SourceView S, TargetView T,
 
 int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                   double* partials, const SolveFusion& fuse, cudaStream_t st) {
-    reduce_kernel<<<kReduceBlocks, 256, 0, st>>>(S, T, cfg, state, cb, partials, fuse);
+    reduce_kernel<<<kReduceBlocks, kReduceThreads, 0, st>>>(S, T, cfg, state, cb, partials, fuse);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }
