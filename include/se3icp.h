@@ -174,11 +174,19 @@ int se3icp_run_sequence(se3icp_ctx* ctx, const double* const* scans, const size_
 
 /* one very large pair (BASELINE.json configs[4]): every rank holds both clouds (se3icp_set_cloud), owns the
  * source query range [src_begin, src_end) for LRF set-up, correspondence search and reduction, and the
- * 29-double normal-equation record is all-reduced once per iteration (plus 4 x 256-bin histograms when the
- * trimmed rejection is active).  All ranks return the identical transform.
+ * 29-double normal-equation record is all-reduced once per iteration.  All ranks return the identical transform.
  * The communicator is either created by the library (se3icp_comm_unique_id on one rank, broadcast the
  * SE3ICP_COMM_ID_BYTES by any means, se3icp_comm_init on every rank; pass nccl_comm = NULL) or supplied by
- * the caller as an ncclComm_t with its rank / size.  NCCL is resolved at run time (dlopen libnccl.so.2). */
+ * the caller as an ncclComm_t with its rank / size.  NCCL is resolved at run time (dlopen libnccl.so.2).
+ * se3icp_comm_init (and the first se3icp_run_sharded with a caller-owned communicator) is collective: besides the
+ * communicator it sets up one 256-byte-per-rank mailbox per context, exchanged as CUDA IPC handles, through which the
+ * ranks of one node all-reduce the record over NVLink peer memory INSIDE the iteration's last kernel — no host round
+ * trip, the loop stays one CUDA graph.  When peer access is not available, when SE3ICP_SHARDED_P2P=0 is set, or when
+ * the trimmed rejection is active (its 4 x 256-bin histograms are summed across ranks between passes), the record goes
+ * through ncclAllReduce from a host-driven loop instead.  A rank whose peers do not show up within 20 s returns
+ * SE3ICP_ERR_NCCL.  se3icp_run_sharded calls must be made by all ranks, the same number of times.
+ * Contiguous ranges of a scan (image bands, laser rings) cost the ranks different amounts of search work; permuting the
+ * source before upload so that every range samples the whole scan (Python: sharding.dealt_order) balances them. */
 #define SE3ICP_COMM_ID_BYTES 128
 int se3icp_comm_unique_id(void* id_out);
 int se3icp_comm_init(se3icp_ctx* ctx, int n_ranks, int rank, const void* id);
