@@ -123,7 +123,9 @@ CorrBuffers se3icp_ctx::corr_buffers(bool with_d2) const {
     cb.keep = keep.as<uint8_t>();
     cb.repair = repair.as<int>();
     cb.work = work.as<int>();
-    cb.ref_q = ref_q.as<double>();
+    cb.ref_iter = ref_iter.as<int>();
+    cb.t_table = t_table.as<double>();
+    cb.t_table_cap = t_table.ptr ? t_table_cap : 0;
     cb.ref_d2nd = ref_d2nd.as<double>();
     // single-launch trimmed rejection whenever no cross-rank histogram exchange is needed
     const bool thr_trim = cfg.trim_active && cfg.n_keep_target > 0 && !sharded;
@@ -212,7 +214,9 @@ int alloc_run(se3icp_ctx* c) {
     SE3_TRY(c->repair.ensure(N * sizeof(int)));
     SE3_TRY(c->d2_nd.ensure(N * sizeof(double)));
     if (cfg.coherence || cfg.coherence_xyz) {
-        SE3_TRY(c->ref_q.ensure(N * 12 * sizeof(double)));
+        SE3_TRY(c->ref_iter.ensure(N * sizeof(int)));
+        c->t_table_cap = (int)std::min<long>(std::max<long>(std::max(cfg.max_iter, cfg.max_se3_iter), 1) + 2, 100000);
+        SE3_TRY(c->t_table.ensure((size_t)c->t_table_cap * 16 * sizeof(double)));
         SE3_TRY(c->ref_d2nd.ensure(N * sizeof(double)));
         SE3_TRY(c->work.ensure(N * sizeof(int)));
     }

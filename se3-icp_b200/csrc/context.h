@@ -19,7 +19,8 @@ struct se3icp_ctx {
     se3::IndexStorage index[2];
     se3::DeviceBuf frame[2], nrm[2], cov[2], conf[2];
     se3::Se3IndexStorage se3idx;
-    se3::DeviceBuf corr_idx, corr_dist, corr_distf, keep, repair, d2_nd, ref_q, ref_d2nd, work;
+    se3::DeviceBuf corr_idx, corr_dist, corr_distf, keep, repair, d2_nd, ref_iter, t_table, ref_d2nd, work;
+    int t_table_cap = 0;
     se3::DeviceBuf psum[2], pmax[2];
     se3::DeviceBuf partials, hist, block_eq, history;
     se3::DeviceBuf state;

@@ -148,7 +148,12 @@ struct CorrBuffers {
     uint8_t* keep;   // [N] trim mask (valid when trim_active)
     int* repair;     // [N] queries needing the exact FP64 repair
     int* work;       // [N] queries the coherence filter could not settle this iteration
-    double* ref_q;   // [12][N] query the remembered second-nearest distance belongs to (coherence filter)
+    // coherence filter: the query a remembered second-nearest distance belongs to is T_ref * X0, and T_ref is the estimate
+    // of the iteration that recorded it — so the iteration number is remembered (4 bytes) instead of the 12-vector
+    // (96 bytes written per searched query, read per filtered query), and the estimates of all iterations are kept
+    int* ref_iter;         // [N]
+    double* t_table;       // [t_table_cap][16] estimate the queries of iteration k were formed with
+    int t_table_cap;
     double* ref_d2nd;  // [N] exact distance to the second-nearest row at that time, < 0 = not known
     // single-pass trimmed rejection (single-GPU runs): the kernels that store a distance also count its key in
     // thist (non-null only then); trim_select turns the histograms into (thr_bits, tie_limit)

@@ -43,6 +43,35 @@ __device__ __forceinline__ void make_query(const SourceView& S, const RunConfig&
     for (int r = 0; r < 3; r++) q[9 + r] = Tm[4 * r] * p[0] + Tm[4 * r + 1] * p[1] + Tm[4 * r + 2] * p[2] + Tm[4 * r + 3];
 }
 
+// |T X0 - T_ref X0|^2 = |(T - T_ref) X0|^2 for source element i: how far its query has moved since the iteration whose
+// estimate was T_ref (coherence certificate).  Formed from the difference of the two estimates, so no second 12-vector is
+// needed; it differs from the distance of the two rounded queries by ~1e-16 |q|, far inside the certificate's slack.
+__device__ __forceinline__ double query_shift_sq(const SourceView& S, const RunConfig& cfg, const double* __restrict__ Tm,
+                                                 const double* __restrict__ Tr, int i) {
+    const size_t n = (size_t)S.n;
+    double D[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) D[k] = Tm[k] - Tr[k];
+    double dl = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double a = S.frame[(3 * c) * n + i] * cfg.alpha, b = S.frame[(3 * c + 1) * n + i] * cfg.alpha,
+                     d = S.frame[(3 * c + 2) * n + i] * cfg.alpha;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double v = D[4 * r] * a + D[4 * r + 1] * b + D[4 * r + 2] * d;
+            dl += v * v;
+        }
+    }
+    const double px = S.x[i] * cfg.beta, py = S.y[i] * cfg.beta, pz = S.z[i] * cfg.beta;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const double v = D[4 * r] * px + D[4 * r + 1] * py + D[4 * r + 2] * pz + D[4 * r + 3];
+        dl += v * v;
+    }
+    return dl;
+}
+
 // exact FP64 squared distance between a query and Morton row j (sequential, non-contracted)
 __device__ __forceinline__ double exact_d2_12(const double q[12], const double* __restrict__ rows64, size_t m, int j) {
     double s = 0.0;
@@ -296,23 +325,27 @@ __device__ __forceinline__ int seed_position_xyz(const CloudIndex& I, double qx,
 //    possibly far in position); and, while the estimate still moves a lot (||T_prev - T||_F > cfg.reseed_thr), whenever
 //    the seed is closer than the remembered match — measured: with the remembered match alone the second pass of a
 //    KITTI-size pair cost more than the cold first one.  The search is exact from any starting point.
-__global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
+__global__ void __launch_bounds__(256, 3) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                          IterState* __restrict__ state, CorrBuffers cb) {
     if (state->done) return;
     const bool se3 = se3_phase_active(cfg, state);
     const bool enabled = (se3 ? cfg.coherence : cfg.coherence_xyz) && state->T_change < cfg.coherence_thr;
+    // first kernel of every iteration: file the estimate this iteration's queries are formed with (certificates recorded
+    // now are checked against it in later iterations)
+    if (blockIdx.x == 0 && threadIdx.x < 16 && cb.t_table && state->iter < cb.t_table_cap)
+        cb.t_table[16 * (size_t)state->iter + threadIdx.x] = state->T_total[threadIdx.x];
     const int t = S.begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S.end) return;
     // spatially sorted processing order: the work list then hands neighbouring queries to neighbouring warps
     const int i = S.order ? S.order[t] : t;
     const double* Tm = state->T_total;
-    const size_t n = (size_t)S.n, m = (size_t)T.n;
+    const size_t m = (size_t)T.n;
     int prev = cb.idx[i];
     const bool have_prev = prev >= 0 && prev < T.n;
     const bool first_icp_pass = !se3 && cfg.has_se3 && state->iter == state->switch_iter;
     const bool want_seed = !have_prev || first_icp_pass || state->T_change > cfg.reseed_thr;
     // the first ICP-phase iteration still sees the 12-D references of the SE(3) phase: ignore them once
-    const bool try_settle = enabled && have_prev && !first_icp_pass && cb.ref_d2nd[i] >= 0.0;
+    const bool try_settle = enabled && have_prev && !first_icp_pass && cb.ref_d2nd[i] >= 0.0;  // (NaN / -1: no certificate)
     if (!try_settle && !want_seed) {
         if (enabled) cb.work[atomicAdd(&state->work_count, 1)] = i;
         return;
@@ -323,12 +356,8 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
         make_query(S, cfg, Tm, i, q);
         double d_prev = -1.0;
         if (try_settle) {
-            double dl = 0.0;
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                double df = q[k] - cb.ref_q[k * n + i];
-                dl += df * df;
-            }
+            // distance to the query the certificate was recorded for: same source element, that iteration's estimate
+            const double dl = query_shift_sq(S, cfg, Tm, cb.t_table + 16 * (size_t)cb.ref_iter[i], i);
             const int j = T.inv12[prev];
             d_prev = exact_d2_12(q, T.rows64, m, j);
             if ((sqrt(d_prev) + sqrt(dl)) * (1.0 + 1e-12) + 1e-300 < cb.ref_d2nd[i]) {
@@ -353,7 +382,10 @@ __global__ void __launch_bounds__(256) nn_filter_kernel(SourceView S, TargetView
         double d_prev = -1.0;
         if (have_prev) d_prev = sqdist3(qx, qy, qz, T.idx.x[prev], T.idx.y[prev], T.idx.z[prev]);
         if (try_settle) {
-            const double ex = qx - cb.ref_q[i], ey = qy - cb.ref_q[n + i], ez = qz - cb.ref_q[2 * n + i];
+            const double* Tr = cb.t_table + 16 * (size_t)cb.ref_iter[i];
+            const double ex = (Tm[0] - Tr[0]) * px + (Tm[1] - Tr[1]) * py + (Tm[2] - Tr[2]) * pz + (Tm[3] - Tr[3]),
+                         ey = (Tm[4] - Tr[4]) * px + (Tm[5] - Tr[5]) * py + (Tm[6] - Tr[6]) * pz + (Tm[7] - Tr[7]),
+                         ez = (Tm[8] - Tr[8]) * px + (Tm[9] - Tr[9]) * py + (Tm[10] - Tr[10]) * pz + (Tm[11] - Tr[11]);
             const double d1 = sqrt(d_prev);
             if ((d1 + sqrt(ex * ex + ey * ey + ez * ez)) * (1.0 + 1e-12) + 1e-300 < cb.ref_d2nd[i]) {
                 store_distance(cfg, cb, i, d1);
@@ -534,13 +566,11 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     traverse_nodes<true>(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
     if (lane == 0) {
         write_se3_match(T, cfg, cb, i, q, best_j, tau);
-        if (cfg.coherence) {
-            cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;
-            if (coherent) {
-                double* qr = cb.ref_q + i;
-#pragma unroll
-                for (int k = 0; k < 12; k++) qr[(size_t)k * S.n] = q[k];
-            }
+        if (cfg.coherence) {  // certificate for later iterations: second-nearest distance + the iteration it belongs to
+            const int it = state->iter;
+            const bool keep = coherent && it < cb.t_table_cap;
+            cb.ref_d2nd[i] = keep ? sqrt(b2) : -1.0;
+            if (keep) cb.ref_iter[i] = it;
         }
     }
 }
@@ -631,11 +661,10 @@ __device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& 
         store_distance(cfg, cb, i, d);  // .cpp:413
         if (cb.d2_nd) cb.d2_nd[i] = tau;
         if (cfg.coherence_xyz) {
-            cb.ref_d2nd[i] = coherent ? sqrt(b2) : -1.0;
-            if (coherent) {
-                double* qr = cb.ref_q + i;
-                qr[0] = qx, qr[(size_t)S.n] = qy, qr[2 * (size_t)S.n] = qz;
-            }
+            const int it = state->iter;
+            const bool keep = coherent && it < cb.t_table_cap;
+            cb.ref_d2nd[i] = keep ? sqrt(b2) : -1.0;
+            if (keep) cb.ref_iter[i] = it;
         }
     }
 }
