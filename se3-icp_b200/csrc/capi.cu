@@ -103,6 +103,7 @@ TargetView se3icp_ctx::target_view() const {
     T.nrm = nrm[1].as<double>();
     T.cov = cov[1].as<double>();
     T.conf = conf[1].as<double>();
+    T.rec = tgt_rec_valid ? tgt_rec.as<double>() : nullptr;
     T.rows32 = se3idx.rows32.as<float4>();
     T.rows64 = se3idx.rows64.as<double>();
     T.box12 = se3idx.box12.as<float2>();
@@ -461,6 +462,12 @@ int enqueue_setup(se3icp_ctx* c) {
         }
         c->feat[w] = key;
     }
+    // one gather record per target point for the reduction (after the features: it holds the normal / covariance)
+    SE3_TRY(c->tgt_rec.ensure((size_t)M * kTargetRecordDoubles * sizeof(double)));
+    SE3_TRY(launch_pack_target_records(c->index[1].view, cfg.variant == SE3ICP_PT2PL ? c->nrm[1].as<double>() : nullptr,
+                                       cfg.variant == SE3ICP_GICP ? c->cov[1].as<double>() : nullptr, c->tgt_rec.as<double>(), st));
+    c->tgt_rec_valid = true;
+    c->launches += 1;
     if (cfg.has_se3)  // .cpp:597-626: weighting, 12 x M matrix and its search structure
         SE3_TRY(c->se3idx.build(c->index[1].view, c->frame[1].as<double>(), cfg.alpha, cfg.with_cf ? 1.0 : cfg.beta, ds, st,
                                 &c->launches));
@@ -1231,6 +1238,7 @@ namespace {
 // without a fresh se3icp_set_cloud fails with SE3ICP_ERR_STATE instead of reading half-overwritten buffers.
 struct StageScope {
     se3icp_ctx* c;
+    explicit StageScope(se3icp_ctx* ctx) : c(ctx) { c->tgt_rec_valid = false; }  // stage data lives in the planes
     ~StageScope() {
         for (int w = 0; w < 2; w++) {
             c->n[w] = 0;

@@ -120,6 +120,9 @@ struct TargetView {
     const double* nrm;    // [3][n] or null
     const double* cov;    // [6][n] or null
     const double* conf;   // [n] or null
+    // what the reduction gathers per correspondence, as ONE 96-byte record per target point (3 sectors instead of the
+    // 3 + 3 / 3 + 6 sectors of the plane layout): x y z | normal(3) or covariance 00 01 02 11 12 22 | padding; or null
+    const double* rec;
     // SE(3) search structure: rows in 6-D Morton order (se3_index.cu); level layout shared with idx
     const float4* rows32; // [3][n]  (alpha R | tscale p) as floats
     const double* rows64; // [12][n]
@@ -244,6 +247,8 @@ int launch_reduce(const SourceView& S, const TargetView& T, const RunConfig& cfg
                   double* partials /*[kReduceBlocks*kReducePartials]*/, const SolveFusion& fuse, cudaStream_t st);
 int launch_trim_select(const RunConfig& cfg, IterState* state, CorrBuffers cb, int begin, int end, cudaStream_t st);
 int launch_trim_stage(const RunConfig& cfg, IterState* state, CorrBuffers cb, int n, cudaStream_t st);
+constexpr int kTargetRecordDoubles = 12;
+int launch_pack_target_records(const CloudIndex& I, const double* nrm, const double* cov, double* rec, cudaStream_t st);
 int launch_sum_partials(const double* partials /*[kReduceBlocks][kReducePartials]*/, double* total /*[kReducePartials]*/,
                         cudaStream_t st);
 int launch_solve_update(const RunConfig& cfg, IterState* state, const double* partials, int n_records, double* history,

@@ -661,6 +661,36 @@ __device__ void kabsch_rotation(const double Sg[3][3], double R[3][3]) {
         for (int c = 0; c < 3; c++) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + d * U[r][2] * V[c][2];
 }
 
+// x y z + normal or covariance of every target point as one 96-byte record (TargetView::rec)
+__global__ void __launch_bounds__(256) pack_target_records_kernel(CloudIndex I, const double* __restrict__ nrm,
+                                                                   const double* __restrict__ cov, double* __restrict__ rec) {
+    const size_t n = (size_t)I.n;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < I.n; j += gridDim.x * blockDim.x) {
+        double r[kTargetRecordDoubles];
+#pragma unroll
+        for (int e = 0; e < kTargetRecordDoubles; e++) r[e] = 0.0;
+        r[0] = I.x[j], r[1] = I.y[j], r[2] = I.z[j];
+        if (cov) {
+#pragma unroll
+            for (int e = 0; e < 6; e++) r[3 + e] = cov[e * n + j];
+        } else if (nrm) {
+#pragma unroll
+            for (int e = 0; e < 3; e++) r[3 + e] = nrm[e * n + j];
+        }
+        double2* o = reinterpret_cast<double2*>(rec + (size_t)j * kTargetRecordDoubles);
+#pragma unroll
+        for (int e = 0; e < kTargetRecordDoubles / 2; e++) o[e] = make_double2(r[2 * e], r[2 * e + 1]);
+    }
+}
+
+int launch_pack_target_records(const CloudIndex& I, const double* nrm, const double* cov, double* rec, cudaStream_t st) {
+    int g = (I.n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    pack_target_records_kernel<<<g, 256, 0, st>>>(I, nrm, cov, rec);
+    SE3_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // fixed-order sum of the per-block records into one record (input of the cross-rank all-reduce)
 __global__ void __launch_bounds__(32) sum_partials_kernel(const double* __restrict__ partials, double* __restrict__ total) {
     int lane = threadIdx.x;
@@ -956,7 +986,14 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(SourceView S, Ta
         const double sx = Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3];
         const double sy = Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7];
         const double sz = Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11];
-        const double tx = T.idx.x[j], ty = T.idx.y[j], tz = T.idx.z[j];
+        const double2* __restrict__ trec = T.rec ? reinterpret_cast<const double2*>(T.rec + (size_t)j * kTargetRecordDoubles) : nullptr;
+        double tx, ty, tz, t3 = 0.0;  // t3: first entry of the normal / covariance, shares a 16-byte load with z
+        if (trec) {
+            const double2 a = trec[0], b = trec[1];
+            tx = a.x, ty = a.y, tz = b.x, t3 = b.y;
+        } else {
+            tx = T.idx.x[j], ty = T.idx.y[j], tz = T.idx.z[j];
+        }
         const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
         acc[28] += 1.0;
         if (cfg.with_cf)
@@ -973,7 +1010,13 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(SourceView S, Ta
             acc[9] += vt * us, acc[10] += vt * vs, acc[11] += vt * ws;
             acc[12] += wt * us, acc[13] += wt * vs, acc[14] += wt * ws;
         } else if (cfg.variant == SE3ICP_PT2PL) {
-            const double nx = T.nrm[j], ny = T.nrm[m + j], nz = T.nrm[2 * m + j];
+            double nx, ny, nz;
+            if (trec) {
+                const double2 c = trec[2];
+                nx = t3, ny = c.x, nz = c.y;
+            } else {
+                nx = T.nrm[j], ny = T.nrm[m + j], nz = T.nrm[2 * m + j];
+            }
             const double r = dx * nx + dy * ny + dz * nz;
             double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
             int o = 0;
@@ -996,6 +1039,14 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(SourceView S, Ta
             for (int r = 0; r < 3; r++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) RC[r][c] = R[r][0] * C[0][c] + R[r][1] * C[1][c] + R[r][2] * C[2][c];
+            double ct[6];  // target covariance
+            if (trec) {
+                const double2 c = trec[2], d = trec[3], f = trec[4];
+                ct[0] = t3, ct[1] = c.x, ct[2] = c.y, ct[3] = d.x, ct[4] = d.y, ct[5] = f.x;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 6; e++) ct[e] = T.cov[e * m + j];
+            }
             double Mm[6];
             {
                 int e = 0;
@@ -1004,7 +1055,7 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(SourceView S, Ta
 #pragma unroll
                     for (int c = r; c < 3; c++) {
                         double v = RC[r][0] * R[c][0] + RC[r][1] * R[c][1] + RC[r][2] * R[c][2];
-                        Mm[e] = v + T.cov[e * m + j];
+                        Mm[e] = v + ct[e];
                         e++;
                     }
             }
