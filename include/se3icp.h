@@ -237,6 +237,30 @@ int se3icp_reduce_gicp(se3icp_ctx* ctx, const double* src, const double* src_cov
 /* a12/a13 tail: LDLT solve of JTJ x = -JTr and the Euler update (Open3D) -> T row-major */
 int se3icp_solve(se3icp_ctx* ctx, const double* in27, double* T_out);
 
+/* ---------------- evaluation helpers either side of the path, on the device ----------------
+ * What the reference's drivers do around a registration with its cc library and Open3D.  Host buffers in and out;
+ * like the stage-level entry points they leave the context without clouds. */
+
+/* cc::error_filterreg (src/cc.cpp:4-20): mean over the source of || T_gt p - T_est p ||.  T row-major 4x4. */
+int se3icp_eval_error_filterreg(se3icp_ctx* ctx, const double* src_xyz, size_t n, const double* T_gt, const double* T_est,
+                                double* error_out);
+/* cc::compute_corrs_with_gt (src/cc.cpp:116-143): index of the target point nearest to T_gt * src[i], exact, ties to the
+ * smaller index.  (cc::compute_nearest_neighbor_correspondences, cc.cpp:220-236, is se3icp_nn_xyz.) */
+int se3icp_eval_corrs_with_gt(se3icp_ctx* ctx, const double* src_xyz, size_t n, const double* tgt_xyz, size_t m,
+                              const double* T_gt, int32_t* tgt_idx);
+/* cc::evaluate_LRF_quality (src/cc.cpp:63-88): mean of angularErrorSO3_alt (cc.cpp:39-61, degrees) between the rotation of
+ * T_gt * source_SE3[pairs[p][0]] and that of target_SE3[pairs[p][1]]; frames as 4x4 row-major matrices (se3icp_lrf /
+ * se3icp_get_se3_cloud layout).  per_pair_error_deg (n_pairs doubles) may be NULL. */
+int se3icp_eval_lrf_quality(se3icp_ctx* ctx, const double* src_frames16, size_t n, const double* tgt_frames16, size_t m,
+                            const double* T_gt, const int32_t* pairs /*[n_pairs][2]*/, size_t n_pairs, double* mean_error_deg,
+                            double* per_pair_error_deg);
+/* Open3D PointCloud::RandomDownSample as examples/benchmark_synthetic.cpp:100,150 uses it: (size_t)(n * ratio) points,
+ * uniformly without replacement, in shuffled order.  The shuffle is a counter-based hash of (seed, index) sorted on the
+ * device, so for a given seed the SUBSET differs from Open3D's mt19937 stream; deterministic for a given seed.
+ * xyz_out ((n * ratio) x 3) and index_out may each be NULL; *n_out receives the count. */
+int se3icp_random_downsample(se3icp_ctx* ctx, const double* xyz, size_t n, double sampling_ratio, uint64_t seed, double* xyz_out,
+                             int32_t* index_out, size_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

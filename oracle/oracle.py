@@ -247,3 +247,35 @@ def eig3(A):
     V = np.zeros((3, 3))
     lib().orc_eig3(_dp(A), _dp(ev), _dp(V))
     return ev, V
+
+
+# --------------------------------------------------------------------------------------------------
+# reference src/cc.cpp evaluation helpers, restated in numpy (test infrastructure for se3icp_eval_*)
+# --------------------------------------------------------------------------------------------------
+def cc_error_filterreg(src, T_gt, T_est):
+    """cc::error_filterreg, src/cc.cpp:4-20: mean || T_gt p - T_est p ||"""
+    src = np.asarray(src, dtype=np.float64)
+    a = src @ T_gt[:3, :3].T + T_gt[:3, 3]
+    b = src @ T_est[:3, :3].T + T_est[:3, 3]
+    return float(np.linalg.norm(a - b, axis=1).sum() / len(src))
+
+
+def cc_angular_error_alt(R1, R2):
+    """cc::angularErrorSO3_alt with safe_acos, src/cc.cpp:39-61, in degrees"""
+    a = (np.trace(R1.T @ R2) - 1.0) / 2.0
+    ang = np.pi if a <= -1.0 else (0.0 if a >= 1.0 else np.arccos(a))
+    return abs(ang) * (180.0 / np.pi)
+
+
+def cc_lrf_quality(src_frames, tgt_frames, T_gt, pairs):
+    """cc::evaluate_LRF_quality, src/cc.cpp:63-88: (mean, per-pair) angular error between T_gt * source frame and target frame"""
+    err = np.array([cc_angular_error_alt((T_gt @ src_frames[i])[:3, :3], tgt_frames[j][:3, :3]) for i, j in pairs])
+    return float(err.sum() / len(pairs)), err
+
+
+def cc_corrs_with_gt(src, tgt, T_gt):
+    """cc::compute_corrs_with_gt, src/cc.cpp:116-143: nearest target point of every T_gt-moved source point (exact;
+    ties to the smaller index like the oracle's kd-tree)"""
+    moved = np.asarray(src, dtype=np.float64) @ T_gt[:3, :3].T + T_gt[:3, 3]
+    idx, _ = nn(moved, np.asarray(tgt, dtype=np.float64))
+    return idx

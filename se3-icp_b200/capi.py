@@ -81,6 +81,7 @@ EXPORTED_SYMBOLS = [
     "se3icp_comm_destroy", "se3icp_comm_info", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
     "se3icp_normals", "se3icp_gicp_cov", "se3icp_nn_se3", "se3icp_nn_xyz", "se3icp_trim", "se3icp_reduce_pt2pt",
     "se3icp_reduce_pt2pl", "se3icp_reduce_gicp", "se3icp_solve",
+    "se3icp_eval_error_filterreg", "se3icp_eval_corrs_with_gt", "se3icp_eval_lrf_quality", "se3icp_random_downsample",
 ]
 
 _lib = None
@@ -275,6 +276,39 @@ class Context:
                                         C.c_void_p(nccl_comm) if nccl_comm else None, int(rank), int(n_ranks), _dp(T),
                                         C.byref(st)))
         return T, st
+
+    # ---- evaluation helpers (reference src/cc.cpp, Open3D RandomDownSample) -------------------------
+    def eval_error_filterreg(self, src, T_gt, T_est):
+        src, Tg, Te = _f64(src), _f64(T_gt), _f64(T_est)
+        out = C.c_double(0)
+        _check(lib().se3icp_eval_error_filterreg(self._h, _dp(src), C.c_size_t(src.shape[0]), _dp(Tg), _dp(Te), C.byref(out)))
+        return out.value
+
+    def eval_corrs_with_gt(self, src, tgt, T_gt):
+        src, tgt, Tg = _f64(src), _f64(tgt), _f64(T_gt)
+        idx = np.zeros(src.shape[0], np.int32)
+        _check(lib().se3icp_eval_corrs_with_gt(self._h, _dp(src), C.c_size_t(src.shape[0]), _dp(tgt), C.c_size_t(tgt.shape[0]),
+                                               _dp(Tg), _ip(idx)))
+        return idx
+
+    def eval_lrf_quality(self, src_frames, tgt_frames, T_gt, pairs):
+        sf, tf, Tg = _f64(src_frames).reshape(-1, 16), _f64(tgt_frames).reshape(-1, 16), _f64(T_gt)
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        mean = C.c_double(0)
+        per = np.zeros(pr.shape[0])
+        _check(lib().se3icp_eval_lrf_quality(self._h, _dp(sf), C.c_size_t(sf.shape[0]), _dp(tf), C.c_size_t(tf.shape[0]), _dp(Tg),
+                                             _ip(pr), C.c_size_t(pr.shape[0]), C.byref(mean), _dp(per)))
+        return mean.value, per
+
+    def random_downsample(self, xyz, ratio, seed=0):
+        xyz = _f64(xyz)
+        n = xyz.shape[0]
+        out = np.zeros((int(n * ratio) + 1, 3))
+        idx = np.zeros(int(n * ratio) + 1, np.int32)
+        k = C.c_size_t(0)
+        _check(lib().se3icp_random_downsample(self._h, _dp(xyz), C.c_size_t(n), C.c_double(ratio), C.c_uint64(seed), _dp(out),
+                                              _ip(idx), C.byref(k)))
+        return out[:k.value], idx[:k.value]
 
     def time_stage(self, stage, repeats=10):
         """average launch duration (ms) of one hot-path kernel on the data of the last run (CUDA events)"""

@@ -38,6 +38,7 @@ struct se3icp_ctx {
     // through CUDA IPC, the device array of all of them, and the run counter that makes sequence words unique
     se3::DeviceBuf mailbox, mailbox_table;
     se3::DeviceBuf knn_list, knn_count;  // compacted query list of a partial kNN / feature pass
+    se3::DeviceBuf eval_buf;             // staging of the evaluation entry points (eval.cu)
     se3::DeviceBuf tgt_rec;              // per-target-point gather record of the reduction (TargetView::rec)
     bool tgt_rec_valid = false;          // ... packed by the current run's set-up (stage-level calls use the planes)
     void* peer_ptr[se3::kMaxPeers] = {nullptr};

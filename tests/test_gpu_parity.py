@@ -686,6 +686,64 @@ def test_swap_clouds_registers_the_inverse_problem(ctx, capi, c1):
 
 
 # ---------------------------------------------------------------------------------------------------
+# Evaluation helpers either side of the path: reference src/cc.cpp and Open3D RandomDownSample.
+def test_eval_helpers_match_the_cc_library(ctx, orc, capi, c1):
+    src, tgt, T_gt = c1
+    rng = np.random.default_rng(3)
+    T_est = W.make_T(W.rot_3d(*rng.uniform(-0.02, 0.02, 3)), rng.uniform(-0.01, 0.01, 3)) @ T_gt
+    # cc::error_filterreg
+    for n in (1, 33, len(src)):
+        g = ctx.eval_error_filterreg(src[:n], T_gt, T_est)
+        assert abs(g - orc.cc_error_filterreg(src[:n], T_gt, T_est)) <= 1e-12 * max(1.0, g)
+    assert ctx.eval_error_filterreg(src, T_gt, T_gt) == 0.0
+    # cc::compute_corrs_with_gt: the fixture's target is T_gt * source point by point (permuted or not): exact NN
+    gi = ctx.eval_corrs_with_gt(src, tgt, T_gt)
+    np.testing.assert_array_equal(gi, orc.cc_corrs_with_gt(src, tgt, T_gt))
+    moved = W.apply_T(T_gt, src)
+    assert np.linalg.norm(moved - tgt[gi], axis=1).max() < 1e-9
+    # cc::evaluate_LRF_quality on the LRFs of both clouds over the ground-truth correspondences
+    fs, ft = ctx.lrf(src, 90), ctx.lrf(tgt, 90)
+    pairs = np.stack([np.arange(len(src)), gi], 1)[::7]
+    g_mean, g_per = ctx.eval_lrf_quality(fs, ft, T_gt, pairs)
+    o_mean, o_per = orc.cc_lrf_quality(fs, ft, T_gt, pairs)
+    ok = np.isfinite(o_per)
+    np.testing.assert_allclose(g_per[ok], o_per[ok], rtol=0, atol=1e-6)  # degrees; acos near 1 amplifies rounding
+    assert np.array_equal(np.isfinite(g_per), ok)
+    if ok.all():
+        assert abs(g_mean - o_mean) < 1e-6
+        # (not small even for this exact copy: the reference's TOLDI centroid sums k/3 - 1 points and divides by k/3,
+        # .cpp:259-265, so the frame depends on where the origin is and is not equivariant under T_gt — the quantity
+        # this metric exists to expose)
+    with pytest.raises(capi.Se3IcpError):
+        ctx.eval_lrf_quality(fs, ft, T_gt, [[0, len(tgt)]])  # pair out of range
+
+
+@pytest.mark.parametrize("ratio", [0.02, 0.5, 1.0, 0.0])
+def test_random_downsample_is_a_uniform_subset(ctx, ratio):
+    """Open3D RandomDownSample as benchmark_synthetic.cpp:100,150 calls it: (size_t)(n * ratio) distinct points, every
+    point equally likely, deterministic for a seed, different for another seed"""
+    pts = W.load_bunny()
+    n = len(pts)
+    sub, idx = ctx.random_downsample(pts, ratio, seed=7)
+    k = int(n * ratio)
+    assert sub.shape == (k, 3) and idx.shape == (k,)
+    if k == 0:
+        return
+    assert len(np.unique(idx)) == k and idx.min() >= 0 and idx.max() < n
+    np.testing.assert_array_equal(sub, pts[idx])
+    sub2, idx2 = ctx.random_downsample(pts, ratio, seed=7)
+    np.testing.assert_array_equal(idx, idx2)
+    if 0 < k < n:
+        _, idx3 = ctx.random_downsample(pts, ratio, seed=8)
+        assert not np.array_equal(idx, idx3)
+        assert not np.array_equal(idx, np.sort(idx))  # shuffled order, as Open3D returns it
+        # uniformity: the chosen indices spread evenly over the index range (chi-square over 16 bins, generous bound)
+        hist = np.histogram(idx, bins=16, range=(0, n))[0]
+        expect = k / 16.0
+        assert ((hist - expect) ** 2 / expect).sum() < 60.0
+
+
+# ---------------------------------------------------------------------------------------------------
 # Ragged and tiny inputs: fewer points than the neighbourhood sizes, unequal cloud sizes, partial last leaves.
 @pytest.mark.parametrize("n_src,n_tgt", [(40, 40), (33, 500), (500, 33), (95, 1000), (1025, 257)])
 @pytest.mark.parametrize("variant", ["pt2pt", "pt2pl", "gicp"])
