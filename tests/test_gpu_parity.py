@@ -565,6 +565,36 @@ def test_graph_loop_equals_host_loop(ctx, capi, bunny4k, entry_name, variant, ov
     assert sb.kernel_launches > 0
 
 
+@pytest.mark.parametrize("n_ctx,n_pairs", [(1, 5), (3, 7), (4, 2), (2, 0)])
+def test_batch_runner_equals_single_runs(capi, n_ctx, n_pairs):
+    """se3icp_run_batch (two enqueue threads walking round-robin over the contexts, asynchronous runs) returns, pair
+    by pair, exactly what a single blocking run returns — more pairs than contexts, fewer, and none; host buffers and
+    device-resident ones"""
+    import torch
+    probs = [W.bunny_problem("easy", seed=20 + i, n_points=3000 + 137 * i) for i in range(n_pairs)]
+    p = capi.default_params(variant="gicp", entry=capi.RUN_SE3_ICP, **dict(RRM, estimated_overlap=0.9))
+    single = []
+    with capi.Context(0) as c:
+        for s, t, _ in probs:
+            c.set_cloud(capi.SOURCE, s)
+            c.set_cloud(capi.TARGET, t)
+            single.append(c.run(p))
+    ctxs = [capi.Context(0) for _ in range(n_ctx)]
+    try:
+        T, st = capi.run_batch(ctxs, [(s, t) for s, t, _ in probs], p)
+        dev = [(torch.from_numpy(np.ascontiguousarray(s)).cuda(), torch.from_numpy(np.ascontiguousarray(t)).cuda()) for s, t, _ in probs]
+        Td, std = capi.run_batch(ctxs, [(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0]) for a, b in dev], p, device_inputs=True)
+    finally:
+        for c in ctxs:
+            c.close()
+    assert T.shape == (n_pairs, 4, 4) and len(st) == n_pairs
+    for k, (Ts, ss) in enumerate(single):
+        np.testing.assert_array_equal(T[k], Ts)
+        np.testing.assert_array_equal(Td[k], Ts)
+        assert st[k].num_iterations == ss.num_iterations == std[k].num_iterations
+        assert st[k].loop_was_graph == 1
+
+
 def test_loop_graph_is_kept_and_updated_in_place(capi, c1, bunny4k):
     """The context instantiates its loop graph once and re-parameterises it for later pairs (other sizes, other
     buffers, other parameters); only another launch sequence (trimming on/off) may build a new executable.  Results
