@@ -456,10 +456,11 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     // Rigorous FP32 lower bound of the squared distance from the query to a node's box.  Per dimension the gap
     // d_k = max(0, lo_k - qf_k, qf_k - hi_k) is rounded down; the true gap (for the FP64 query) is at least
     // (d_k - qeps)+, and sum (d_k - qeps)+^2 >= S - 2 qeps sum d_k >= S - 2 sqrt(12) qeps sqrt(S) with S = sum d_k^2
-    // (Cauchy-Schwarz), so the rounding of the query costs one correction per node instead of two operations per
-    // dimension.  S is accumulated with round-down FMAs; S - c sqrt(S) grows with S wherever it is positive, so the
-    // smaller computed S keeps the bound valid.  Two dimensions per 16-byte load (box12_slot).
-    const float qcorr = __fmul_ru(7.f, qeps);  // > 2 sqrt(12) qeps
+    // (Cauchy-Schwarz) >= k1 S - k2 (sqrt(S) <= (S + 1) / 2: no square root, traverse.cuh rounding_correction), so the
+    // rounding of the query costs two operations per node instead of two per dimension.  S is accumulated with round-down
+    // FMAs; k1 S - k2 grows with S, so the smaller computed S keeps the bound valid.  Two dimensions per 16-byte load.
+    float qk1, qk2;
+    rounding_correction(__fmul_ru(7.f, qeps), qk1, qk2);  // 7 qeps > 2 sqrt(12) qeps
     auto lb_fn = [&](int node) -> double {
         const float4* b = reinterpret_cast<const float4*>(T.box12) + node;
         float acc = 0.f;
@@ -471,7 +472,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
             acc = __fmaf_rd(d0, d0, acc);  // exact d*d + acc rounded down: still a lower bound, one instruction
             acc = __fmaf_rd(d1, d1, acc);
         }
-        return (double)fmaxf(0.f, __fsub_rd(acc, __fmul_ru(qcorr, __fsqrt_ru(acc))));
+        return (double)fmaxf(0.f, __fsub_rd(__fmul_rd(acc, qk1), qk2));
     };
 
     // ---- temporal coherence (DESIGN.md "coherence filter") -----------------------------------------------

@@ -14,21 +14,28 @@ constexpr int kStackEntries = 192;  // >= 31 * levels + 1 for up to 6 levels (n 
 // FP32 image of a 3-D query for the box tests: the coordinates rounded to float and a correction term covering that
 // rounding (see box_lower_bound)
 struct BoxQuery {
-    float x, y, z, corr;
+    float x, y, z, k1, k2;
 };
+
+// c > 2 sqrt(dims) eps bounds the effect of rounding the query to FP32 on sum d_k (see box_lower_bound); with
+// sqrt(S) <= (S + 1) / 2 the correction c sqrt(S) needs no square root: S - c sqrt(S) >= S (1 - c/2) - c/2 = k1 S - k2.
+__device__ __forceinline__ void rounding_correction(float c, float& k1, float& k2) {
+    k2 = __fmul_ru(0.5f, c);
+    k1 = __fsub_rd(1.0f, k2);
+}
 
 __device__ __forceinline__ BoxQuery make_box_query(double qx, double qy, double qz) {
     BoxQuery q;
     q.x = (float)qx, q.y = (float)qy, q.z = (float)qz;
-    // |q_k - float(q_k)| <= 2^-24 |q_k| <= eps := 2^-23 max|q|; corr > 2 sqrt(3) eps
-    q.corr = __fmul_ru(3.5f * 1.1920929e-07f, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z)));
+    // |q_k - float(q_k)| <= 2^-24 |q_k| <= eps := 2^-23 max|q|; c > 2 sqrt(3) eps
+    rounding_correction(__fmul_ru(3.5f * 1.1920929e-07f, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z))), q.k1, q.k2);
     return q;
 }
 
 // Rigorous FP32 lower bound of the squared distance from the (FP64) query to a node's box, the boxes being rounded
 // outwards: per axis the gap d_k = max(0, lo_k - qf_k, qf_k - hi_k) is rounded down, the true gap is at least
-// (d_k - eps)+, and sum (d_k - eps)+^2 >= S - 2 eps sum d_k >= S - 2 sqrt(3) eps sqrt(S) with S = sum d_k^2.
-// S - c sqrt(S) grows with S wherever it is positive, so accumulating S with round-down FMAs keeps the bound valid.
+// (d_k - eps)+, and sum (d_k - eps)+^2 >= S - 2 eps sum d_k >= S - 2 sqrt(3) eps sqrt(S) >= k1 S - k2 with S = sum d_k^2
+// (rounding_correction).  k1 S - k2 grows with S, so accumulating S with round-down FMAs keeps the bound valid.
 __device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node, const BoxQuery& q) {
     const float2* b = I.box + node;
     const size_t tn = (size_t)I.total_nodes;
@@ -37,7 +44,7 @@ __device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node,
     const float dy = fmaxf(fmaxf(__fsub_rd(by.x, q.y), __fsub_rd(q.y, by.y)), 0.f);
     const float dz = fmaxf(fmaxf(__fsub_rd(bz.x, q.z), __fsub_rd(q.z, bz.y)), 0.f);
     const float s = __fmaf_rd(dz, dz, __fmaf_rd(dy, dy, __fmul_rd(dx, dx)));
-    return (double)fmaxf(0.f, __fsub_rd(s, __fmul_ru(q.corr, __fsqrt_ru(s))));
+    return (double)fmaxf(0.f, __fsub_rd(__fmul_rd(s, q.k1), q.k2));
 }
 
 // `tau` is read on every test, so the leaf functor may shrink it while the traversal runs.
