@@ -564,7 +564,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
         skip_leaf = first;
     }
     // prune against the second-best bound when it is being tracked
-    traverse_nodes<true>(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
+    traverse_nodes<true, false>(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
     if (lane == 0) {
         write_se3_match(T, cfg, cb, i, q, best_j, tau);
         if (cfg.coherence) {  // certificate for later iterations: second-nearest distance + the iteration it belongs to
