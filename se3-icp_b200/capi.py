@@ -10,6 +10,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libse3icp_cuda.so")
+# development hook: A/B timing of kernel variants built by profiles/experiments/build_variant.sh
+if os.environ.get("SE3ICP_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["SE3ICP_LIB"])
 
 PT2PT, PT2PL, GICP = 0, 1, 2
 RUN_ICP, RUN_SE3_ICP, RUN_SE3_ICP_CF, RUN_SE3_PURE = 0, 1, 2, 3

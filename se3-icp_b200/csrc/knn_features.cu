@@ -18,6 +18,13 @@ constexpr int kKnnWarps = 16;  // 16 warps x 2 blocks per SM at 64 registers: 1.
                                // latency of the serial selection loops better than 24 do, spills included
 constexpr int kPool = 256;  // unsorted candidate pool per warp
 
+#ifndef KNN_INTERP
+#define KNN_INTERP 1
+#endif
+#ifndef KNN_POSPOOL
+#define KNN_POSPOOL 1
+#endif
+
 struct KnnScratch {
     unsigned long long d[kPool];
     int id[kPool];
@@ -225,10 +232,67 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
     // once, at the end, on the ~K survivors.
     int pool = 0;
     double tau = inf;
+    // exact (distance, ORIGINAL index) cut of the pool (rare: ties); the pool itself carries Morton positions
+    auto exact_trim = [&](int count, int keep) -> double {
+#if KNN_POSPOOL
+        for (int t = lane; t < count; t += 32) W.id[t] = I.perm[W.id[t]];
+        __syncwarp();
+#endif
+        const double r = knn_exact_trim(W.d, W.id, count, keep, lane);
+#if KNN_POSPOOL
+        for (int t = lane; t < keep; t += 32) W.id[t] = I.inv[W.id[t]];
+        __syncwarp();
+#endif
+        return r;
+    };
     auto shrink_pool = [&]() {
         if (pool <= K + 24) return;
         double e[8];
         int eid[8];
+#if KNN_INTERP
+        // Bounds of the bisection need not be tight: 0 below, the current radius above (every pool entry passed d2 <= tau);
+        // on the first shrink (no radius yet) the largest high word + 1, one integer warp reduction.
+        unsigned hmax = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int t = lane + 32 * k;
+            e[k] = inf;
+            eid[k] = 0;
+            if (t < pool) {
+                e[k] = __longlong_as_double((long long)W.d[t]);
+                eid[k] = W.id[t];
+                hmax = max(hmax, (unsigned)__double2hiint(e[k]));
+            }
+        }
+        double lo = 0.0, hi = tau;
+        if (!(tau < inf)) hi = __hiloint2double((int)(__reduce_max_sync(SE3_FULL, hmax) + 1u), 0);
+        // Squared distances of points on a surface are spread almost uniformly, so interpolating the count (regula falsi
+        // on the empirical distribution, aimed at the middle of the accepted window K .. K + 24) needs 2-3 rounds where
+        // halving the interval needs 6-8; every other round from the fourth on halves, which bounds the worst case.
+        int c_lo = 0, c_hi = pool;
+        for (int it = 0; it < 24; it++) {
+            double mid;
+            if (it < 3 || (it & 1)) {
+                const float f = __fdividef((float)(K + 12 - c_lo), (float)(c_hi - c_lo));
+                mid = fma(hi - lo, (double)f, lo);
+            } else {
+                mid = 0.5 * (lo + hi);
+            }
+            if (!(mid > lo && mid < hi)) break;
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) c += e[k] <= mid ? 1 : 0;
+            c = __reduce_add_sync(SE3_FULL, c);
+            if (c < K) {
+                lo = mid;
+                c_lo = c;
+            } else {
+                hi = mid;
+                c_hi = c;
+                if (c <= K + 24) break;
+            }
+        }
+#else
         double lo = inf, hi = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -257,6 +321,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
                 if (c <= K + 24) break;
             }
         }
+#endif
         __syncwarp();
         int out = 0;
 #pragma unroll
@@ -274,7 +339,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         tau = hi;
         __syncwarp();
         if (pool > K + 24) {  // ties at the threshold (pool >= K holds, so the K-th entry exists)
-            tau = knn_exact_trim(W.d, W.id, pool, K, lane);
+            tau = exact_trim(pool, K);
             pool = K;
         }
     };
@@ -285,7 +350,11 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         int id = 0x7fffffff;
         if (p < I.n) {
             d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
+#if KNN_POSPOOL
+            id = p;  // Morton position: no index load here, and the neighbour gathers below hit the sorted planes
+#else
             id = I.perm[p];
+#endif
             pass = d2 <= tau;
         }
         unsigned m = __ballot_sync(SE3_FULL, pass);
@@ -316,7 +385,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         // exact order of the survivors (K .. K + 24 of them): the list is striped over the warp, element e in lane
         // e % 32, register e / 32
         if (pool > 128) {  // K + 24 > 128: cut to exactly K first
-            tau = knn_exact_trim(W.d, W.id, pool, K, lane);
+            tau = exact_trim(pool, K);
             pool = K;
         }
         unsigned int w[4];
@@ -330,7 +399,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
                 }
             }
         } else {  // equal quantised keys somewhere: the 96-bit network decides, sorted entries come back in the pool
-            knn_exact_trim(W.d, W.id, pool, pool, lane);
+            exact_trim(pool, pool);
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 const int j = lane + 32 * t;
@@ -348,7 +417,11 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         for (int t = 0; t < 4; t++) {
             int j = lane + 32 * t;
             if (j < fa.K) {
+#if KNN_POSPOOL
+                fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? I.perm[Li[t]] : -1;
+#else
                 fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? Li[t] : -1;
+#endif
                 if (fa.knn_d2) fa.knn_d2[(size_t)self * fa.K + j] = j < cnt ? __longlong_as_double((long long)Ld[t]) : -1.0;
             }
         }
@@ -363,9 +436,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         nx[t] = ny[t] = nz[t] = 0.0;
         if (j < cnt && active) {
             int id = Li[t];
+#if KNN_POSPOOL
+            nx[t] = I.sx[id];
+            ny[t] = I.sy[id];
+            nz[t] = I.sz[id];
+#else
             nx[t] = I.x[id];
             ny[t] = I.y[id];
             nz[t] = I.z[id];
+#endif
         }
     }
     const size_t n = (size_t)I.n;
