@@ -80,6 +80,9 @@ __device__ __forceinline__ void warp_argmin(double& d2, int& idx) {
     }
 }
 
+#ifndef EIG_FAST_ROTATION
+#define EIG_FAST_ROTATION 1
+#endif
 // ---- 3x3 symmetric eigen-solver (cyclic Jacobi, FP64) ----------------------------------------------
 // a = {a00,a01,a02,a11,a12,a22}.  evals ascending; V columns are unit eigenvectors (V[r][c]).
 __device__ inline void eig3_sym(const double a[6], double evals[3], double V[3][3]) {
@@ -97,10 +100,23 @@ __device__ inline void eig3_sym(const double a[6], double evals[3], double V[3][
 #pragma unroll
             for (int q = p + 1; q < 3; q++) {
                 double apq = A[p][q];
+#if EIG_FAST_ROTATION
+                // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = d / apq, d = (aqq - app) / 2, written as
+                // sgn(d) apq / (|d| + sqrt(d^2 + apq^2)): one square root, one division and one reciprocal square root on
+                // the dependent chain instead of two divisions, two square roots and a reciprocal (the solve of a block is
+                // a serial latency chain the other warps wait for)
+                const double d = 0.5 * (A[q][q] - A[p][p]);
+                const double h = sqrt(d * d + apq * apq);
+                if (apq != 0.0 && h > 0.0) {
+                    double t = apq / (fabs(d) + h);
+                    if (d < 0.0) t = -t;
+                    double c = rsqrt(t * t + 1.0), s = t * c;
+#else
                 if (apq != 0.0) {
                     double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
                     double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                     double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#endif
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
                         double akp = A[k][p], akq = A[k][q];

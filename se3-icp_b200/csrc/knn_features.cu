@@ -18,12 +18,10 @@ constexpr int kKnnWarps = 16;  // 16 warps x 2 blocks per SM at 64 registers: 1.
                                // latency of the serial selection loops better than 24 do, spills included
 constexpr int kPool = 256;  // unsorted candidate pool per warp
 
-#ifndef KNN_INTERP
-#define KNN_INTERP 1
+#ifndef KNN_QPW
+#define KNN_QPW 1
 #endif
-#ifndef KNN_POSPOOL
-#define KNN_POSPOOL 1
-#endif
+constexpr int kQpw = KNN_QPW;  // queries per warp between two block barriers
 
 struct KnnScratch {
     unsigned long long d[kPool];
@@ -204,411 +202,404 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
     extern __shared__ __align__(16) unsigned char knn_smem[];  // dynamic: more than 48 KB from 12 warps per block on
     KnnScratch* scratch = reinterpret_cast<KnnScratch*>(knn_smem);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    // query = Morton position s: warp w takes position w, or entry w of the compacted list of a partial range.  Warps past
-    // the end redo the last query without writing, so the whole block reaches the __syncthreads() of the batched
-    // eigen-solves below.
-    const int w_raw = blockIdx.x * kKnnWarps + wib;
+    // query = Morton position s: warp w takes positions kQpw w .. kQpw w + kQpw - 1, or those entries of the compacted list
+    // of a partial range.  Warps past the end redo the last query without writing, so the whole block reaches the
+    // __syncthreads() of the batched eigen-solves below.
     const int n_queries = fa.active_count ? *fa.active_count : I.n;
-    if (blockIdx.x * kKnnWarps >= n_queries) return;  // block-uniform
-    const bool in_range = w_raw < n_queries;
-    const int s = !in_range ? I.n - 1 : (fa.active_list ? fa.active_list[w_raw] : w_raw);
+    if (blockIdx.x * (kKnnWarps * kQpw) >= n_queries) return;  // block-uniform
     KnnScratch& W = scratch[wib];
-
-    const double qx = I.sx[s], qy = I.sy[s], qz = I.sz[s];
-    const int self = I.perm[s];
-    // sharded source: only the rank's own range of original indices is processed; block-uniform exit
-    // is not possible (neighbouring Morton positions belong to different ranks), so foreign queries
-    // fall through as inactive warps
-    const bool active = in_range && self >= fa.q_begin && self < fa.q_end;
     const int K = fa.K < I.n ? fa.K : I.n;
-    key_t Ld[4] = {kInfKey, kInfKey, kInfKey, kInfKey};
-    int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
     const int n_leaves = I.level_cnt[0];
     const double inf = __longlong_as_double((long long)kInfKey);
-
-    // Search phase: candidates within the current radius go to an UNSORTED pool in shared memory.  When the
-    // pool fills up, a bisection on the distance value (8 compares + ballots per step, no data movement)
-    // finds a radius that keeps between K and K+24 of them and the pool is compacted.  Sorting happens
-    // once, at the end, on the ~K survivors.
-    int pool = 0;
-    double tau = inf;
-    // exact (distance, ORIGINAL index) cut of the pool (rare: ties); the pool itself carries Morton positions
-    auto exact_trim = [&](int count, int keep) -> double {
-#if KNN_POSPOOL
-        for (int t = lane; t < count; t += 32) W.id[t] = I.perm[W.id[t]];
-        __syncwarp();
-#endif
-        const double r = knn_exact_trim(W.d, W.id, count, keep, lane);
-#if KNN_POSPOOL
-        for (int t = lane; t < keep; t += 32) W.id[t] = I.inv[W.id[t]];
-        __syncwarp();
-#endif
-        return r;
-    };
-    auto shrink_pool = [&]() {
-        if (pool <= K + 24) return;
-        double e[8];
-        int eid[8];
-#if KNN_INTERP
-        // Bounds of the bisection need not be tight: 0 below, the current radius above (every pool entry passed d2 <= tau);
-        // on the first shrink (no radius yet) the largest high word + 1, one integer warp reduction.
-        unsigned hmax = 0u;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int t = lane + 32 * k;
-            e[k] = inf;
-            eid[k] = 0;
-            if (t < pool) {
-                e[k] = __longlong_as_double((long long)W.d[t]);
-                eid[k] = W.id[t];
-                hmax = max(hmax, (unsigned)__double2hiint(e[k]));
-            }
-        }
-        double lo = 0.0, hi = tau;
-        if (!(tau < inf)) hi = __hiloint2double((int)(__reduce_max_sync(SE3_FULL, hmax) + 1u), 0);
-        // Squared distances of points on a surface are spread almost uniformly, so interpolating the count (regula falsi
-        // on the empirical distribution, aimed at the middle of the accepted window K .. K + 24) needs 2-3 rounds where
-        // halving the interval needs 6-8; every other round from the fourth on halves, which bounds the worst case.
-        int c_lo = 0, c_hi = pool;
-        for (int it = 0; it < 24; it++) {
-            double mid;
-            if (it < 3 || (it & 1)) {
-                const float f = __fdividef((float)(K + 12 - c_lo), (float)(c_hi - c_lo));
-                mid = fma(hi - lo, (double)f, lo);
-            } else {
-                mid = 0.5 * (lo + hi);
-            }
-            if (!(mid > lo && mid < hi)) break;
-            int c = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) c += e[k] <= mid ? 1 : 0;
-            c = __reduce_add_sync(SE3_FULL, c);
-            if (c < K) {
-                lo = mid;
-                c_lo = c;
-            } else {
-                hi = mid;
-                c_hi = c;
-                if (c <= K + 24) break;
-            }
-        }
-#else
-        double lo = inf, hi = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int t = lane + 32 * k;
-            e[k] = inf;
-            eid[k] = 0;
-            if (t < pool) {
-                e[k] = __longlong_as_double((long long)W.d[t]);
-                eid[k] = W.id[t];
-                lo = fmin(lo, e[k]);
-                hi = fmax(hi, e[k]);
-            }
-        }
-        lo = warp_min(lo);
-        hi = warp_max(hi);  // count(d <= hi) = pool >= K always holds for hi
-        for (int it = 0; it < 14; it++) {
-            double mid = 0.5 * (lo + hi);
-            if (!(mid > lo && mid < hi)) break;
-            int c = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) c += __popc(__ballot_sync(SE3_FULL, e[k] <= mid));
-            if (c < K) {
-                lo = mid;
-            } else {
-                hi = mid;
-                if (c <= K + 24) break;
-            }
-        }
-#endif
-        __syncwarp();
-        int out = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            bool keep = e[k] <= hi;  // padding is +inf and hi is finite
-            unsigned m = __ballot_sync(SE3_FULL, keep);
-            if (keep) {
-                int pos = out + __popc(m & ((1u << lane) - 1u));
-                W.d[pos] = (key_t)__double_as_longlong(e[k]);
-                W.id[pos] = eid[k];
-            }
-            out += __popc(m);
-        }
-        pool = out;
-        tau = hi;
-        __syncwarp();
-        if (pool > K + 24) {  // ties at the threshold (pool >= K holds, so the K-th entry exists)
-            tau = exact_trim(pool, K);
-            pool = K;
-        }
-    };
-    auto eval_leaf = [&](int leaf) {
-        int p = leaf * 32 + lane;
-        bool pass = false;
-        double d2 = inf;
-        int id = 0x7fffffff;
-        if (p < I.n) {
-            d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
-#if KNN_POSPOOL
-            id = p;  // Morton position: no index load here, and the neighbour gathers below hit the sorted planes
-#else
-            id = I.perm[p];
-#endif
-            pass = d2 <= tau;
-        }
-        unsigned m = __ballot_sync(SE3_FULL, pass);
-        if (m == 0u) return;
-        if (pass) {
-            int pos = pool + __popc(m & ((1u << lane) - 1u));
-            W.d[pos] = (key_t)__double_as_longlong(d2);
-            W.id[pos] = id;
-        }
-        pool += __popc(m);
-        __syncwarp();
-        if (pool > kPool - 32) shrink_pool();
-    };
-
-    // seed: the leaves around the query in Morton order give a near-final search radius
-    const int L = s >> 5;
-    const int half = (K + 63) / 64;
-    const int w0 = L - half > 0 ? L - half : 0;
-    const int w1 = L + half < n_leaves - 1 ? L + half : n_leaves - 1;
-    if (active) {
-        for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
-        shrink_pool();
-        traverse_boxes<false>(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
-            if (leaf >= w0 && leaf <= w1) return;
-            eval_leaf(leaf);
-        });
-        shrink_pool();
-        // exact order of the survivors (K .. K + 24 of them): the list is striped over the warp, element e in lane
-        // e % 32, register e / 32
-        if (pool > 128) {  // K + 24 > 128: cut to exactly K first
-            tau = exact_trim(pool, K);
-            pool = K;
-        }
-        unsigned int w[4];
-        if (sort_pool_quantised(W.d, pool, lane, w)) {
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (w[t] != 0xffffffffu) {
-                    const int slot = (int)(w[t] & 127u);
-                    Ld[t] = W.d[slot];
-                    Li[t] = W.id[slot];
-                }
-            }
-        } else {  // equal quantised keys somewhere: the 96-bit network decides, sorted entries come back in the pool
-            exact_trim(pool, pool);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int j = lane + 32 * t;
-                if (j < pool) {
-                    Ld[t] = W.d[j];
-                    Li[t] = W.id[j];
-                }
-            }
-        }
-    }
-    const int cnt = K;  // the list now holds the min(K, n) nearest, ascending, then padding
-
-    if (fa.knn_idx && active) {
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            int j = lane + 32 * t;
-            if (j < fa.K) {
-#if KNN_POSPOOL
-                fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? I.perm[Li[t]] : -1;
-#else
-                fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? Li[t] : -1;
-#endif
-                if (fa.knn_d2) fa.knn_d2[(size_t)self * fa.K + j] = j < cnt ? __longlong_as_double((long long)Ld[t]) : -1.0;
-            }
-        }
-    }
-    if (fa.k_lrf <= 0 && fa.k_nrm <= 0) return;
-
-    // neighbour coordinates, list position j = lane + 32 t
-    double nx[4], ny[4], nz[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        int j = lane + 32 * t;
-        nx[t] = ny[t] = nz[t] = 0.0;
-        if (j < cnt && active) {
-            int id = Li[t];
-#if KNN_POSPOOL
-            nx[t] = I.sx[id];
-            ny[t] = I.sy[id];
-            nz[t] = I.sz[id];
-#else
-            nx[t] = I.x[id];
-            ny[t] = I.y[id];
-            nz[t] = I.z[id];
-#endif
-        }
-    }
     const size_t n = (size_t)I.n;
-
-    // ---- phase A: per-warp second moments; the 3x3 eigen-solves of the whole block are then done by
-    //      16 threads at once (one instruction stream instead of 16 redundant warp-wide ones)
-    __shared__ double eig_in[kKnnWarps][2][6];
-    __shared__ double eig_out[kKnnWarps][2][3];
-    __shared__ int eig_valid[kKnnWarps];
-    if (lane == 0) eig_valid[wib] = active ? 1 : 0;
+    const int cnt = K;  // a finished list holds the min(K, n) nearest, ascending, then padding
     const int cl = fa.k_lrf > 0 ? (fa.k_lrf < cnt ? fa.k_lrf : cnt) : 0;
     const int rz = cl / 3;
     const int cn = fa.k_nrm > 0 ? (fa.k_nrm < cnt ? fa.k_nrm : cnt) : 0;
-    if (fa.k_lrf > 0 && active) {
-        // .cpp:259-265 centroid of neighbours 1..rz-1 divided by rz
-        double cx = 0, cy = 0, cz = 0;
+
+    // per-block hand-over to the batched 3x3 eigen-solves (one thread per system instead of one redundant warp-wide
+    // instruction stream per query); with kQpw > 1 the sorted neighbour positions and the radius wait in shared memory
+    __shared__ double eig_in[kKnnWarps][kQpw][2][6];
+    __shared__ double eig_out[kKnnWarps][kQpw][2][3];
+    __shared__ int eig_valid[kKnnWarps][kQpw];
+    __shared__ int nb_pos[kQpw > 1 ? kKnnWarps : 1][kQpw > 1 ? kQpw : 1][kQpw > 1 ? 128 : 1];
+    __shared__ double nb_radius2[kKnnWarps][kQpw];
+
+    // state of the query in flight
+    int s = 0, self = 0;
+    bool active = false;
+    double qx = 0, qy = 0, qz = 0;
+    double nx[4], ny[4], nz[4];  // neighbour coordinates, list position j = lane + 32 t
+
+    auto select_query = [&](int qi) {
+        const int w_raw = (blockIdx.x * kKnnWarps + wib) * kQpw + qi;
+        const bool in_range = w_raw < n_queries;
+        s = !in_range ? I.n - 1 : (fa.active_list ? fa.active_list[w_raw] : w_raw);
+        qx = I.sx[s], qy = I.sy[s], qz = I.sz[s];
+        self = I.perm[s];
+        // sharded source: only the rank's own range of original indices is processed; block-uniform exit
+        // is not possible (neighbouring Morton positions belong to different ranks), so foreign queries
+        // fall through as inactive warps
+        active = in_range && self >= fa.q_begin && self < fa.q_end;
+    };
+    auto gather_neighbours = [&](const int (&Li)[4]) {
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             int j = lane + 32 * t;
-            if (j >= 1 && j < rz) {
-                cx += nx[t];
-                cy += ny[t];
-                cz += nz[t];
+            nx[t] = ny[t] = nz[t] = 0.0;
+            if (j < cnt && active) {
+                int id = Li[t];  // Morton position: the gathers hit the sorted planes the search has just read
+                nx[t] = I.sx[id];
+                ny[t] = I.sy[id];
+                nz[t] = I.sz[id];
             }
         }
-        double inv_rz = 1.0 / (double)rz;
-        cx = warp_sum(cx) * inv_rz;
-        cy = warp_sum(cy) * inv_rz;
-        cz = warp_sum(cz) * inv_rz;
-        // .cpp:268-272 scatter of neighbours 1..rz
-        double c6[6] = {0, 0, 0, 0, 0, 0};
+    };
+
+    // ---- search + second moments of one query ------------------------------------------------------------------------
+    auto search_query = [&](int qi) {
+        key_t Ld[4] = {kInfKey, kInfKey, kInfKey, kInfKey};
+        int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+        // Search phase: candidates within the current radius go to an UNSORTED pool in shared memory.  When the
+        // pool fills up, a search on the distance value (compares + one integer warp reduction per step, no data
+        // movement) finds a radius that keeps between K and K+24 of them and the pool is compacted.  Sorting happens
+        // once, at the end, on the ~K survivors.
+        int pool = 0;
+        double tau = inf;
+        // exact (distance, ORIGINAL index) cut of the pool (rare: ties); the pool itself carries Morton positions
+        auto exact_trim = [&](int count, int keep) -> double {
+            for (int t = lane; t < count; t += 32) W.id[t] = I.perm[W.id[t]];
+            __syncwarp();
+            const double r = knn_exact_trim(W.d, W.id, count, keep, lane);
+            for (int t = lane; t < keep; t += 32) W.id[t] = I.inv[W.id[t]];
+            __syncwarp();
+            return r;
+        };
+        auto shrink_pool = [&]() {
+            if (pool <= K + 24) return;
+            double e[8];
+            int eid[8];
+            // Bounds of the search need not be tight: 0 below, the current radius above (every pool entry passed
+            // d2 <= tau); on the first shrink (no radius yet) the largest high word + 1, one integer warp reduction.
+            unsigned hmax = 0u;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            int j = lane + 32 * t;
-            if (j >= 1 && j <= rz && j < cnt) {
-                double dx = nx[t] - cx, dy = ny[t] - cy, dz = nz[t] - cz;
-                c6[0] += dx * dx;
-                c6[1] += dx * dy;
-                c6[2] += dx * dz;
-                c6[3] += dy * dy;
-                c6[4] += dy * dz;
-                c6[5] += dz * dz;
+            for (int k = 0; k < 8; k++) {
+                int t = lane + 32 * k;
+                e[k] = inf;
+                eid[k] = 0;
+                if (t < pool) {
+                    e[k] = __longlong_as_double((long long)W.d[t]);
+                    eid[k] = W.id[t];
+                    hmax = max(hmax, (unsigned)__double2hiint(e[k]));
+                }
+            }
+            double lo = 0.0, hi = tau;
+            if (!(tau < inf)) hi = __hiloint2double((int)(__reduce_max_sync(SE3_FULL, hmax) + 1u), 0);
+            // Squared distances of points on a surface are spread almost uniformly, so interpolating the count (regula
+            // falsi on the empirical distribution, aimed at the middle of the accepted window K .. K + 24) needs 2-3
+            // rounds where halving the interval needs 6-8; every other round from the fourth on halves, which bounds
+            // the worst case.  count(d <= hi) >= K holds throughout.
+            int c_lo = 0, c_hi = pool;
+            for (int it = 0; it < 24; it++) {
+                double mid;
+                if (it < 3 || (it & 1)) {
+                    const float f = __fdividef((float)(K + 12 - c_lo), (float)(c_hi - c_lo));
+                    mid = fma(hi - lo, (double)f, lo);
+                } else {
+                    mid = 0.5 * (lo + hi);
+                }
+                if (!(mid > lo && mid < hi)) break;
+                int c = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) c += e[k] <= mid ? 1 : 0;
+                c = __reduce_add_sync(SE3_FULL, c);
+                if (c < K) {
+                    lo = mid;
+                    c_lo = c;
+                } else {
+                    hi = mid;
+                    c_hi = c;
+                    if (c <= K + 24) break;
+                }
+            }
+            __syncwarp();
+            int out = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                bool keep = e[k] <= hi;  // padding is +inf and hi is finite
+                unsigned m = __ballot_sync(SE3_FULL, keep);
+                if (keep) {
+                    int pos = out + __popc(m & ((1u << lane) - 1u));
+                    W.d[pos] = (key_t)__double_as_longlong(e[k]);
+                    W.id[pos] = eid[k];
+                }
+                out += __popc(m);
+            }
+            pool = out;
+            tau = hi;
+            __syncwarp();
+            if (pool > K + 24) {  // ties at the threshold (pool >= K holds, so the K-th entry exists)
+                tau = exact_trim(pool, K);
+                pool = K;
+            }
+        };
+        auto eval_leaf = [&](int leaf) {
+            int p = leaf * 32 + lane;
+            bool pass = false;
+            double d2 = inf;
+            if (p < I.n) {
+                d2 = sqdist3(qx, qy, qz, I.sx[p], I.sy[p], I.sz[p]);
+                pass = d2 <= tau;
+            }
+            unsigned m = __ballot_sync(SE3_FULL, pass);
+            if (m == 0u) return;
+            if (pass) {
+                int pos = pool + __popc(m & ((1u << lane) - 1u));
+                W.d[pos] = (key_t)__double_as_longlong(d2);
+                W.id[pos] = p;  // Morton position: no index load here
+            }
+            pool += __popc(m);
+            __syncwarp();
+            if (pool > kPool - 32) shrink_pool();
+        };
+
+        // seed: the leaves around the query in Morton order give a near-final search radius
+        const int L = s >> 5;
+        const int half = (K + 63) / 64;
+        const int w0 = L - half > 0 ? L - half : 0;
+        const int w1 = L + half < n_leaves - 1 ? L + half : n_leaves - 1;
+        if (active) {
+            for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
+            shrink_pool();
+            traverse_boxes<false>(I, qx, qy, qz, tau, W.stack, lane, [&](int leaf) {
+                if (leaf >= w0 && leaf <= w1) return;
+                eval_leaf(leaf);
+            });
+            shrink_pool();
+            // exact order of the survivors (K .. K + 24 of them): the list is striped over the warp, element e in lane
+            // e % 32, register e / 32
+            if (pool > 128) {  // K + 24 > 128: cut to exactly K first
+                tau = exact_trim(pool, K);
+                pool = K;
+            }
+            unsigned int w[4];
+            if (sort_pool_quantised(W.d, pool, lane, w)) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (w[t] != 0xffffffffu) {
+                        const int slot = (int)(w[t] & 127u);
+                        Ld[t] = W.d[slot];
+                        Li[t] = W.id[slot];
+                    }
+                }
+            } else {  // equal quantised keys somewhere: the 96-bit network decides, sorted entries come back in the pool
+                exact_trim(pool, pool);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int j = lane + 32 * t;
+                    if (j < pool) {
+                        Ld[t] = W.d[j];
+                        Li[t] = W.id[j];
+                    }
+                }
+            }
+            __syncwarp();  // the pool is reused by the warp's next query
+        }
+
+        if (fa.knn_idx && active) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j < fa.K) {
+                    fa.knn_idx[(size_t)self * fa.K + j] = j < cnt ? I.perm[Li[t]] : -1;
+                    if (fa.knn_d2) fa.knn_d2[(size_t)self * fa.K + j] = j < cnt ? __longlong_as_double((long long)Ld[t]) : -1.0;
+                }
             }
         }
+        if (fa.k_lrf <= 0 && fa.k_nrm <= 0) return;
+
+        gather_neighbours(Li);
+        if (kQpw > 1) {
 #pragma unroll
-        for (int e = 0; e < 6; e++) {
-            double v = warp_sum(c6[e]);
-            if (lane == 0) eig_in[wib][0][e] = v;
+            for (int t = 0; t < 4; t++) nb_pos[wib][qi][lane + 32 * t] = Li[t];
         }
+        if (lane == 0) eig_valid[wib][qi] = active ? 1 : 0;
+        if (fa.k_lrf > 0 && active) {
+            key_t rad_bits;
+            int rad_id;
+            list_at(Ld, Li, cl - 1, rad_bits, rad_id);
+            if (lane == 0) nb_radius2[wib][qi] = __longlong_as_double((long long)rad_bits);
+            // .cpp:259-265 centroid of neighbours 1..rz-1 divided by rz
+            double cx = 0, cy = 0, cz = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j >= 1 && j < rz) {
+                    cx += nx[t];
+                    cy += ny[t];
+                    cz += nz[t];
+                }
+            }
+            double inv_rz = 1.0 / (double)rz;
+            cx = warp_sum(cx) * inv_rz;
+            cy = warp_sum(cy) * inv_rz;
+            cz = warp_sum(cz) * inv_rz;
+            // .cpp:268-272 scatter of neighbours 1..rz
+            double c6[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j >= 1 && j <= rz && j < cnt) {
+                    double dx = nx[t] - cx, dy = ny[t] - cy, dz = nz[t] - cz;
+                    c6[0] += dx * dx;
+                    c6[1] += dx * dy;
+                    c6[2] += dx * dz;
+                    c6[3] += dy * dy;
+                    c6[4] += dy * dz;
+                    c6[5] += dz * dz;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 6; e++) {
+                double v = warp_sum(c6[e]);
+                if (lane == 0) eig_in[wib][qi][0][e] = v;
+            }
+        }
+        if (fa.k_nrm > 0 && cn >= 3 && active) {
+            // Open3D ComputeCovariance: cumulants over the neighbourhood including the point itself
+            double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j < cn) {
+                    cu[0] += nx[t];
+                    cu[1] += ny[t];
+                    cu[2] += nz[t];
+                    cu[3] += nx[t] * nx[t];
+                    cu[4] += nx[t] * ny[t];
+                    cu[5] += nx[t] * nz[t];
+                    cu[6] += ny[t] * ny[t];
+                    cu[7] += ny[t] * nz[t];
+                    cu[8] += nz[t] * nz[t];
+                }
+            }
+            double invc = 1.0 / (double)cn;
+#pragma unroll
+            for (int e = 0; e < 9; e++) cu[e] = warp_sum(cu[e]) * invc;
+            if (lane == 0) {
+                eig_in[wib][qi][1][0] = cu[3] - cu[0] * cu[0];
+                eig_in[wib][qi][1][1] = cu[4] - cu[0] * cu[1];
+                eig_in[wib][qi][1][2] = cu[5] - cu[0] * cu[2];
+                eig_in[wib][qi][1][3] = cu[6] - cu[1] * cu[1];
+                eig_in[wib][qi][1][4] = cu[7] - cu[1] * cu[2];
+                eig_in[wib][qi][1][5] = cu[8] - cu[2] * cu[2];
+            }
+        }
+    };
+
+    // ---- frame / normal / covariance of one query from the solved eigenvectors --------------------------------------
+    auto finish_query = [&](int qi) {
+        if (!active) return;
+        if (fa.k_lrf > 0) {
+            const double radius = sqrt(nb_radius2[wib][qi]);  // .cpp:256
+            double zx = eig_out[wib][qi][0][0], zy = eig_out[wib][qi][0][1], zz = eig_out[wib][qi][0][2];
+            // .cpp:286-297
+            double ax = 0, ay = 0, az = 0, wx = 0, wy = 0, wz = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                int j = lane + 32 * t;
+                if (j >= 1 && j < cl) {
+                    double vx = nx[t] - qx, vy = ny[t] - qy, vz = nz[t] - qz;
+                    ax += vx;
+                    ay += vy;
+                    az += vz;
+                    double nd = zx * vx + zy * vy + zz * vz;
+                    double an = sqrt(vx * vx + vy * vy + vz * vz);
+                    double w = (radius - an) * (radius - an) * (nd * nd);
+                    wx += w * vx;
+                    wy += w * vy;
+                    wz += w * vz;
+                }
+            }
+            ax = warp_sum(ax);
+            ay = warp_sum(ay);
+            az = warp_sum(az);
+            wx = warp_sum(wx);
+            wy = warp_sum(wy);
+            wz = warp_sum(wz);
+            if (zx * ax + zy * ay + zz * az < 0.0) {  // .cpp:298
+                zx = -zx;
+                zy = -zy;
+                zz = -zz;
+            }
+            double pd = wx * zx + wy * zy + wz * zz;  // .cpp:302-303
+            double xx = wx - pd * zx, xy = wy - pd * zy, xz = wz - pd * zz;
+            double inv = 1.0 / sqrt(xx * xx + xy * xy + xz * xz);
+            xx *= inv;
+            xy *= inv;
+            xz *= inv;
+            double yx = zy * xz - zz * xy, yy = zz * xx - zx * xz, yz = zx * xy - zy * xx;  // y = z x x (.cpp:306)
+            if (lane == 0) {
+                double* f = fa.frame + self;
+                f[0] = xx, f[n] = xy, f[2 * n] = xz;
+                f[3 * n] = yx, f[4 * n] = yy, f[5 * n] = yz;
+                f[6 * n] = zx, f[7 * n] = zy, f[8 * n] = zz;
+            }
+        }
+
+        if (fa.k_nrm > 0 && lane == 0) {
+            double nvx = 0.0, nvy = 0.0, nvz = 1.0;  // fewer than 3 neighbours: Open3D's identity covariance -> (0,0,1)
+            if (cn >= 3) {
+                nvx = eig_out[wib][qi][1][0], nvy = eig_out[wib][qi][1][1], nvz = eig_out[wib][qi][1][2];
+                if (nvx * nvx + nvy * nvy + nvz * nvz == 0.0) {
+                    nvx = 0.0, nvy = 0.0, nvz = 1.0;
+                }
+            }
+            if (fa.nrm) {
+                fa.nrm[self] = nvx;
+                fa.nrm[n + self] = nvy;
+                fa.nrm[2 * n + self] = nvz;
+            }
+            if (fa.want_cov && fa.cov) {
+                double C6[6];
+                gicp_cov_from_normal(nvx, nvy, nvz, fa.gicp_eps, C6);
+                double* o = fa.cov + self;
+                for (int e = 0; e < 6; e++) o[e * n] = C6[e];
+            }
+        }
+    };
+
+#pragma unroll 1
+    for (int qi = 0; qi < kQpw; qi++) {
+        select_query(qi);
+        search_query(qi);
     }
-    if (fa.k_nrm > 0 && cn >= 3 && active) {
-        // Open3D ComputeCovariance: cumulants over the neighbourhood including the point itself
-        double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            int j = lane + 32 * t;
-            if (j < cn) {
-                cu[0] += nx[t];
-                cu[1] += ny[t];
-                cu[2] += nz[t];
-                cu[3] += nx[t] * nx[t];
-                cu[4] += nx[t] * ny[t];
-                cu[5] += nx[t] * nz[t];
-                cu[6] += ny[t] * ny[t];
-                cu[7] += ny[t] * nz[t];
-                cu[8] += nz[t] * nz[t];
-            }
-        }
-        double invc = 1.0 / (double)cn;
-#pragma unroll
-        for (int e = 0; e < 9; e++) cu[e] = warp_sum(cu[e]) * invc;
-        if (lane == 0) {
-            eig_in[wib][1][0] = cu[3] - cu[0] * cu[0];
-            eig_in[wib][1][1] = cu[4] - cu[0] * cu[1];
-            eig_in[wib][1][2] = cu[5] - cu[0] * cu[2];
-            eig_in[wib][1][3] = cu[6] - cu[1] * cu[1];
-            eig_in[wib][1][4] = cu[7] - cu[1] * cu[2];
-            eig_in[wib][1][5] = cu[8] - cu[2] * cu[2];
-        }
-    }
+    if (fa.k_lrf <= 0 && fa.k_nrm <= 0) return;
     __syncthreads();
-    if (threadIdx.x < 2 * kKnnWarps) {
-        int w = threadIdx.x >> 1, which = threadIdx.x & 1;
-        if (eig_valid[w] && ((which == 0 && fa.k_lrf > 0) || (which == 1 && fa.k_nrm > 0))) {
+    if (threadIdx.x < 2 * kKnnWarps * kQpw) {
+        const int which = threadIdx.x & 1, qi = (threadIdx.x >> 1) % kQpw, w = threadIdx.x / (2 * kQpw);
+        if (eig_valid[w][qi] && ((which == 0 && fa.k_lrf > 0) || (which == 1 && fa.k_nrm > 0))) {
             double a6[6], ev[3], V[3][3];
 #pragma unroll
-            for (int e = 0; e < 6; e++) a6[e] = eig_in[w][which][e];
+            for (int e = 0; e < 6; e++) a6[e] = eig_in[w][qi][which][e];
             eig3_sym(a6, ev, V);  // .cpp:275-281 / Open3D ComputeNormal: eigenvector of the smallest eigenvalue
-            eig_out[w][which][0] = V[0][0];
-            eig_out[w][which][1] = V[1][0];
-            eig_out[w][which][2] = V[2][0];
+            eig_out[w][qi][which][0] = V[0][0];
+            eig_out[w][qi][which][1] = V[1][0];
+            eig_out[w][qi][which][2] = V[2][0];
         }
     }
     __syncthreads();
-    if (!active) return;
-
-    if (fa.k_lrf > 0) {
-        key_t rad_bits;
-        int rad_id;
-        list_at(Ld, Li, cl - 1, rad_bits, rad_id);
-        const double radius = sqrt(__longlong_as_double((long long)rad_bits));  // .cpp:256
-        double zx = eig_out[wib][0][0], zy = eig_out[wib][0][1], zz = eig_out[wib][0][2];
-        // .cpp:286-297
-        double ax = 0, ay = 0, az = 0, wx = 0, wy = 0, wz = 0;
+    if (kQpw == 1) {
+        finish_query(0);  // the neighbour coordinates are still in registers
+    } else {
+#pragma unroll 1
+        for (int qi = 0; qi < kQpw; qi++) {
+            select_query(qi);
+            int Li[4];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            int j = lane + 32 * t;
-            if (j >= 1 && j < cl) {
-                double vx = nx[t] - qx, vy = ny[t] - qy, vz = nz[t] - qz;
-                ax += vx;
-                ay += vy;
-                az += vz;
-                double nd = zx * vx + zy * vy + zz * vz;
-                double an = sqrt(vx * vx + vy * vy + vz * vz);
-                double w = (radius - an) * (radius - an) * (nd * nd);
-                wx += w * vx;
-                wy += w * vy;
-                wz += w * vz;
-            }
-        }
-        ax = warp_sum(ax);
-        ay = warp_sum(ay);
-        az = warp_sum(az);
-        wx = warp_sum(wx);
-        wy = warp_sum(wy);
-        wz = warp_sum(wz);
-        if (zx * ax + zy * ay + zz * az < 0.0) {  // .cpp:298
-            zx = -zx;
-            zy = -zy;
-            zz = -zz;
-        }
-        double pd = wx * zx + wy * zy + wz * zz;  // .cpp:302-303
-        double xx = wx - pd * zx, xy = wy - pd * zy, xz = wz - pd * zz;
-        double inv = 1.0 / sqrt(xx * xx + xy * xy + xz * xz);
-        xx *= inv;
-        xy *= inv;
-        xz *= inv;
-        double yx = zy * xz - zz * xy, yy = zz * xx - zx * xz, yz = zx * xy - zy * xx;  // y = z x x (.cpp:306)
-        if (lane == 0) {
-            double* f = fa.frame + self;
-            f[0] = xx, f[n] = xy, f[2 * n] = xz;
-            f[3 * n] = yx, f[4 * n] = yy, f[5 * n] = yz;
-            f[6 * n] = zx, f[7 * n] = zy, f[8 * n] = zz;
-        }
-    }
-
-    if (fa.k_nrm > 0 && lane == 0) {
-        double nvx = 0.0, nvy = 0.0, nvz = 1.0;  // fewer than 3 neighbours: Open3D's identity covariance -> (0,0,1)
-        if (cn >= 3) {
-            nvx = eig_out[wib][1][0], nvy = eig_out[wib][1][1], nvz = eig_out[wib][1][2];
-            if (nvx * nvx + nvy * nvy + nvz * nvz == 0.0) {
-                nvx = 0.0, nvy = 0.0, nvz = 1.0;
-            }
-        }
-        if (fa.nrm) {
-            fa.nrm[self] = nvx;
-            fa.nrm[n + self] = nvy;
-            fa.nrm[2 * n + self] = nvz;
-        }
-        if (fa.want_cov && fa.cov) {
-            double C6[6];
-            gicp_cov_from_normal(nvx, nvy, nvz, fa.gicp_eps, C6);
-            double* o = fa.cov + self;
-            for (int e = 0; e < 6; e++) o[e * n] = C6[e];
+            for (int t = 0; t < 4; t++) Li[t] = nb_pos[wib][qi][lane + 32 * t];
+            gather_neighbours(Li);
+            finish_query(qi);
         }
     }
 }
@@ -657,7 +648,7 @@ int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t
         set_last_error("cloud too large for the traversal stack");
         return SE3ICP_ERR_UNSUPPORTED;
     }
-    int blocks = (I.n + kKnnWarps - 1) / kKnnWarps;
+    int blocks = (I.n + kKnnWarps * kQpw - 1) / (kKnnWarps * kQpw);
     const size_t smem = sizeof(KnnScratch) * kKnnWarps;
     static bool configured[64] = {false};  // function attributes are per device
     int dev = 0;
