@@ -151,10 +151,11 @@ public:
         indices.clear();
         distance2.clear();
         for (auto& h : heap) {
+            if (!(h.first < radius * radius)) continue;  // nanoflann's RadiusResultSet::addPoint keeps dist < radius^2 (strict)
             indices.push_back(h.second);
             distance2.push_back(h.first);
         }
-        return (int)heap.size();
+        return (int)indices.size();
     }
 
 private:

@@ -56,7 +56,7 @@ public:
     double alpha_rot;             // 3.0   rotation weight of the SE(3) metric
     double beta_transl;           // 1.0   translation weight
     double scale_preprocessing;   // 3.0   clouds are scaled to this radius
-    double lrf_radius_;           // 0.8   SHOT frame radius (unused by every entry point, kept for compatibility)
+    double lrf_radius_;           // 0.8   SHOT frame radius (used only after set_use_shot_lrf(true), as in the reference)
 
     // ================= results of a run_*() call ====================================================================
     Eigen::Matrix4d current_estimated_T_;          // source -> target, original coordinates
@@ -116,6 +116,9 @@ public:
     void set_trim_keep_largest(bool on) { trim_keep_largest_ = on; }  // false: keep the smallest distances instead of PCL's
                                                                       // `distance >` comparator (include/se3icp.h)
     void set_device(int device);                                      // CUDA ordinal (default: SE3ICP_DEVICE or 0)
+    // true: lift points with the SHOT frame (radius lrf_radius_, reference .cpp:121-239) instead of the TOLDI frame —
+    // what un-commenting the reference's calls at .cpp:593-594 / :812-813 would do (LRF ablations)
+    void set_use_shot_lrf(bool on) { use_shot_lrf_ = on; }
 
 private:
     se3icp_ctx* context();
@@ -126,4 +129,5 @@ private:
     int device_ = -1;
     bool mirror_state_ = false;
     bool trim_keep_largest_ = true;
+    bool use_shot_lrf_ = false;
 };

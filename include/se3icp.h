@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SE3ICP_ABI_VERSION 3
+#define SE3ICP_ABI_VERSION 4
 
 enum se3icp_status {
     SE3ICP_OK = 0,
@@ -59,6 +59,13 @@ enum se3icp_nn_mode {
 
 enum se3icp_which { SE3ICP_SOURCE = 0, SE3ICP_TARGET = 1 };
 
+/* local reference frame that lifts a point to an SE(3) element */
+enum se3icp_lrf_method {
+    SE3ICP_LRF_TOLDI = 0, /* kNN support, .cpp:241-331: what every entry point of the reference runs */
+    SE3ICP_LRF_SHOT = 1   /* radius support, .cpp:121-239: the reference's dormant alternative (its calls are commented out
+                             at .cpp:593-594,812-813); LRF ablations */
+};
+
 /* POD mirror of the public configuration fields of IterativeSE3Registration
  * (reference hpp:80-95; defaults .cpp:334-348). */
 typedef struct se3icp_params {
@@ -89,6 +96,12 @@ typedef struct se3icp_params {
                                        context (se3icp_swap_clouds, se3icp_run_sequence); 0 = recompute every run.
                                        se3icp_set_cloud / se3icp_set_cloud_device always invalidate them, so a caller who
                                        rewrites a caller-owned device buffer in place must set the cloud again */
+    int32_t lrf_method;             /* se3icp_lrf_method; 0 = TOLDI (default) */
+    int32_t reserved0;
+    double lrf_radius;              /* 0.8 (reference lrf_radius_, .cpp:340): support radius of the SHOT frame, in the
+                                       NORMALISED cloud's units (.cpp:568-582), as the commented call sites pass it.  SHOT
+                                       frames depend on that per-pair scale, so they are never reused across runs, and
+                                       se3icp_run_sharded does not take them */
 } se3icp_params;
 
 typedef struct se3icp_stats {
@@ -211,6 +224,11 @@ int se3icp_time_stage(se3icp_ctx* ctx, int stage, int repeats, double* ms_avg);
 int se3icp_knn(se3icp_ctx* ctx, const double* xyz, size_t n, int k, int32_t* idx, double* d2);
 /* a4: TOLDI LRF (.cpp:241-331).  frames[n*16] row-major [x y z p; 0 0 0 1] */
 int se3icp_lrf(se3icp_ctx* ctx, const double* xyz, size_t n, int k, double* frames);
+/* f4: SHOT LRF with radius support (.cpp:121-239, the reference's dormant alternative to TOLDI; `lrf_radius_` .cpp:340).
+ * frames[n*16] as se3icp_lrf.  A point with fewer than 5 others inside the radius gets the identity rotation (undefined
+ * in the reference).  *unresolved_ties (may be NULL): median votes (.cpp:189-197) that could not be decided because more
+ * than ~100 support points share one distance; 0 on real data. */
+int se3icp_shot_lrf(se3icp_ctx* ctx, const double* xyz, size_t n, double radius, double* frames, int64_t* unresolved_ties);
 /* a6: Open3D EstimateNormals(KNN(k)).  normals[n*3], unoriented */
 int se3icp_normals(se3icp_ctx* ctx, const double* xyz, size_t n, int k, double* normals);
 /* a6: GICP covariances from normals (.cpp:4-14,45-51).  cov[n*9] row-major */

@@ -34,6 +34,9 @@ class Params(C.Structure):
         ("beta_transl", C.c_double),
         ("scale_preprocessing", C.c_double),
         ("gicp_epsilon", C.c_double),
+        ("lrf_method", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("lrf_radius", C.c_double),
     ]
 
 
@@ -160,6 +163,15 @@ def toldi(xyz, k):
     n = xyz.shape[0]
     fr = np.zeros((n, 4, 4))
     lib().orc_toldi(_dp(xyz), C.c_size_t(n), int(k), _dp(fr))
+    return fr
+
+
+def shot(xyz, radius):
+    """SHOT LRF with radius support (reference .cpp:121-239): n x 4x4 frames [x y z p]"""
+    xyz = _c64(xyz)
+    n = xyz.shape[0]
+    fr = np.zeros((n, 4, 4))
+    lib().orc_shot(_dp(xyz), C.c_size_t(n), C.c_double(radius), _dp(fr))
     return fr
 
 

@@ -13,6 +13,9 @@
 // defined (external linkage, not declared in the header) in the reference's src/iterative_SE3_registration.cpp:318-331
 void computeAllTOLDISE3FramesOMP(const open3d::geometry::PointCloud& cloud, const open3d::geometry::KDTreeFlann& kdtree_for_LRF,
                                  int knn_pts, std::vector<Eigen::Matrix4d>& result_frames);
+// reference .cpp:226-239 (same linkage; its call sites in the class are commented out, .cpp:593-594)
+void computeAllSHOTSE3FramesOMP(const open3d::geometry::PointCloud& cloud, const open3d::geometry::KDTreeFlann& kdtree_for_LRF,
+                                double radius, std::vector<Eigen::Matrix4d>& result_frames);
 // reference .cpp:33-52
 void InitializePointCloudForGeneralizedICP_modified(open3d::geometry::PointCloud& pcd, double epsilon);
 
@@ -90,6 +93,16 @@ int ref_toldi(const double* xyz, size_t n, int knn, double* frames) {
     open3d::geometry::KDTreeFlann tree(pc);
     std::vector<Eigen::Matrix4d> out;
     computeAllTOLDISE3FramesOMP(pc, tree, knn, out);
+    for (size_t i = 0; i < n; i++) store_row_major(out[i], frames + 16 * i);
+    return 0;
+}
+
+// SHOT frames of every point with the reference's own functions (.cpp:121-239); frames: n x 4x4 row-major
+int ref_shot(const double* xyz, size_t n, double radius, double* frames) {
+    open3d::geometry::PointCloud pc = make_cloud(xyz, n);
+    open3d::geometry::KDTreeFlann tree(pc);
+    std::vector<Eigen::Matrix4d> out;
+    computeAllSHOTSE3FramesOMP(pc, tree, radius, out);
     for (size_t i = 0; i < n; i++) store_row_major(out[i], frames + 16 * i);
     return 0;
 }

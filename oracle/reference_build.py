@@ -98,6 +98,14 @@ def toldi(xyz, knn):
     return fr
 
 
+def shot(xyz, radius):
+    """computeAllSHOTSE3FramesOMP of the reference source (.cpp:226-239)"""
+    xyz = _c64(xyz)
+    fr = np.zeros((len(xyz), 4, 4))
+    lib().ref_shot(_dp(xyz), C.c_size_t(len(xyz)), C.c_double(radius), _dp(fr))
+    return fr
+
+
 def gicp_cov(xyz, eps=1e-3):
     xyz = _c64(xyz)
     nrm = np.zeros((len(xyz), 3))

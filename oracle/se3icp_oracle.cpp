@@ -236,6 +236,23 @@ public:
         return (int)s.count;
     }
 
+    // every point with d2 < r2 (nanoflann's RadiusResultSet::addPoint: strict), ascending by (d2, idx) — Open3D
+    // KDTreeFlann::SearchRadius (sorted = true); call site reference .cpp:136
+    void radius(const double* q, double r2, std::vector<Neighbor>& out) const {
+        out.clear();
+        if (n_ == 0) return;
+        std::vector<double> side(dim_, 0.0);
+        double mind = 0.0;
+        for (int d = 0; d < dim_; d++) {
+            double v = q[d];
+            if (v < lo_[d]) side[d] = (v - lo_[d]) * (v - lo_[d]);
+            if (v > hi_[d]) side[d] = (v - hi_[d]) * (v - hi_[d]);
+            mind += side[d];
+        }
+        radius_rec(0, mind, side.data(), q, r2, out);
+        std::sort(out.begin(), out.end(), nb_less);
+    }
+
 private:
     static constexpr int kLeaf = 15;
     struct Node {
@@ -293,6 +310,35 @@ private:
         nodes_[id].left = l;
         nodes_[id].right = r;
         return id;
+    }
+
+    void radius_rec(int id, double mind, double* side, const double* q, double r2, std::vector<Neighbor>& out) const {
+        const Node& nd = nodes_[id];
+        if (nd.split_dim < 0) {
+            for (int i = nd.left; i < nd.right; i++) {
+                int pi = perm_[i];
+                const double* p = &pts_[(size_t)pi * dim_];
+                double d2 = 0.0;
+                for (int d = 0; d < dim_; d++) {
+                    double df = q[d] - p[d];
+                    d2 += df * df;
+                }
+                if (d2 < r2) out.push_back(Neighbor{d2, pi});
+            }
+            return;
+        }
+        int d = nd.split_dim;
+        double dl = q[d] - nd.split_lo, dh = q[d] - nd.split_hi;
+        int near = dl + dh < 0.0 ? nd.left : nd.right, far = dl + dh < 0.0 ? nd.right : nd.left;
+        double cut = dl + dh < 0.0 ? dh * dh : dl * dl;
+        radius_rec(near, mind, side, q, r2, out);
+        double saved = side[d];
+        double far_mind = mind + cut - saved;
+        if (far_mind * (1.0 - 1e-12) <= r2) {
+            side[d] = cut;
+            radius_rec(far, far_mind, side, q, r2, out);
+            side[d] = saved;
+        }
     }
 
     inline double worst(const Search& s) const {
@@ -479,6 +525,77 @@ void toldi_all(const Cloud& cloud, const KDTree& tree, int knn_pts, std::vector<
         std::vector<Neighbor> nb;
 #pragma omp for schedule(dynamic, 64)
         for (long i = 0; i < (long)n; i++) frames[i] = toldi_frame(cloud, tree, cloud.p(i), knn_pts, nb);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SHOT local reference frame, radius variant — reference .cpp:121-224 (single), :226-239 (loop).  The reference keeps it
+// as an alternative to TOLDI (its calls are commented out at .cpp:593-594,812-813; `lrf_radius_` .cpp:340).
+//   support   = points with d2 < radius^2, ascending; entry 0 (the centre itself) is skipped              .cpp:136,151
+//   M         = sum (radius - d_i) a_i a_i^T / sum (radius - d_i),  a_i = p_i - centre                     .cpp:151-157
+//   x+, z+    = eigenvectors of the largest / smallest eigenvalue                                            .cpp:169-170
+//   sign      = majority of a_i . v >= 0; on an exact tie the 5 neighbours around the median distance vote   .cpp:172-214
+//   y         = z x x                                                                                        .cpp:216
+// Fewer than 5 support points: the reference only prints a warning and then divides 0 / 0 or reads diff_vectors out of
+// range on a tie; that case is not defined there, and this restatement (like the CUDA path) returns the identity rotation.
+// ----------------------------------------------------------------------------------------------
+M4 shot_frame(const Cloud& cloud, const KDTree& tree, int index_center, double radius, std::vector<Neighbor>& nb,
+              std::vector<V3>& diff) {
+    V3 center = cloud.p(index_center);
+    double q[3] = {center.x, center.y, center.z};
+    tree.radius(q, radius * radius, nb);
+    M4 F = m4_identity();
+    F(0, 3) = center.x, F(1, 3) = center.y, F(2, 3) = center.z;
+    int n_considered = (int)nb.size() - 1;
+    if (n_considered < 5) return F;
+    M3 cov = m3_zero();
+    double total = 0.0;
+    diff.clear();
+    for (size_t i = 1; i < nb.size(); i++) {
+        double w = radius - std::sqrt(nb[i].d2);
+        V3 a = cloud.p(nb[i].idx) - center;
+        diff.push_back(a);
+        double av[3] = {a.x, a.y, a.z};
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) cov(r, c) += w * av[r] * av[c];
+        total += w;
+    }
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) cov(r, c) /= total;
+    double ev[3];
+    M3 V;
+    eig3_sym(cov, ev, V);
+    V3 axis[2] = {{V(0, 2), V(1, 2), V(2, 2)}, {V(0, 0), V(1, 0), V(2, 0)}};  // x+ (largest), z+ (smallest)
+    for (int k = 0; k < 2; k++) {
+        int plus = 0;
+        for (const V3& a : diff)
+            if (dot(a, axis[k]) >= 0.0) plus++;
+        int s = 2 * plus - n_considered;
+        if (s == 0) {
+            const int points = 5, median = n_considered / 2;
+            for (int i = -points / 2; i <= points / 2; i++)
+                if (dot(diff[median - i], axis[k]) >= 0.0) s++;
+            if (s < points / 2 + 1) axis[k] = -1.0 * axis[k];
+        } else if (s < 0) {
+            axis[k] = -1.0 * axis[k];
+        }
+    }
+    V3 x = axis[0], z = axis[1], y = cross(z, x);
+    F(0, 0) = x.x, F(1, 0) = x.y, F(2, 0) = x.z;
+    F(0, 1) = y.x, F(1, 1) = y.y, F(2, 1) = y.z;
+    F(0, 2) = z.x, F(1, 2) = z.y, F(2, 2) = z.z;
+    return F;
+}
+
+void shot_all(const Cloud& cloud, const KDTree& tree, double radius, std::vector<M4>& frames) {
+    size_t n = cloud.size();
+    frames.resize(n);
+#pragma omp parallel
+    {
+        std::vector<Neighbor> nb;
+        std::vector<V3> diff;
+#pragma omp for schedule(dynamic, 64)
+        for (long i = 0; i < (long)n; i++) frames[i] = shot_frame(cloud, tree, (int)i, radius, nb, diff);
     }
 }
 
@@ -1009,8 +1126,13 @@ int run_se3(Cloud& source, Cloud& source_moving, Cloud& target, const orc_params
     tree_s.build(source.pts.data(), n, 3);
     tree_t.build(target.pts.data(), m, 3);
     std::vector<M4> src_se3, tgt_se3;
-    toldi_all(source, tree_s, P.number_of_nn_for_LRF, src_se3);
-    toldi_all(target, tree_t, P.number_of_nn_for_LRF, tgt_se3);
+    if (P.lrf_method == 1) {  // .cpp:593-594 (commented out in the reference)
+        shot_all(source, tree_s, P.lrf_radius, src_se3);
+        shot_all(target, tree_t, P.lrf_radius, tgt_se3);
+    } else {
+        toldi_all(source, tree_s, P.number_of_nn_for_LRF, src_se3);
+        toldi_all(target, tree_t, P.number_of_nn_for_LRF, tgt_se3);
+    }
 
     // .cpp:597-607 rotation block * alpha, translation column * beta
     auto weight = [&](std::vector<M4>& v) {
@@ -1141,6 +1263,9 @@ void orc_default_params(orc_params* p) {  // reference ctor .cpp:334-348
     p->beta_transl = 1.0;
     p->scale_preprocessing = 3.0;
     p->gicp_epsilon = 1e-3;
+    p->lrf_method = 0;
+    p->reserved0 = 0;
+    p->lrf_radius = 0.8;
 }
 
 int orc_num_threads(void) {
@@ -1206,6 +1331,17 @@ int orc_toldi(const double* xyz, size_t n, int k, double* frames) {
     tree.build(xyz, n, 3);
     std::vector<M4> f;
     toldi_all(c, tree, k, f);
+    for (size_t i = 0; i < n; i++) std::memcpy(&frames[16 * i], f[i].a, sizeof(f[i].a));
+    return 0;
+}
+
+int orc_shot(const double* xyz, size_t n, double radius, double* frames) {
+    Cloud c;
+    fill_cloud(c, xyz, n);
+    KDTree tree;
+    tree.build(xyz, n, 3);
+    std::vector<M4> f;
+    shot_all(c, tree, radius, f);
     for (size_t i = 0; i < n; i++) std::memcpy(&frames[16 * i], f[i].a, sizeof(f[i].a));
     return 0;
 }

@@ -57,6 +57,9 @@ typedef struct orc_params {
     double beta_transl;               /* 1.0 */
     double scale_preprocessing;       /* 3.0 */
     double gicp_epsilon;              /* 1e-3 */
+    int32_t lrf_method;               /* 0 = TOLDI (.cpp:590-591), 1 = SHOT (the commented calls .cpp:593-594,812-813) */
+    int32_t reserved0;
+    double lrf_radius;                /* 0.8 (.cpp:340), in the normalised cloud's units */
 } orc_params;
 
 typedef struct orc_stats {
@@ -96,6 +99,8 @@ int orc_run(const double* src_xyz, size_t n, const double* tgt_xyz, size_t m, co
 int orc_knn_self(const double* xyz, size_t n, int k, int32_t* idx, double* d2);
 /* TOLDI LRF (reference .cpp:241-331): frames[n*16] row-major 4x4 [x y z p; 0 0 0 1] */
 int orc_toldi(const double* xyz, size_t n, int k, double* frames);
+/* SHOT LRF, radius support (reference .cpp:121-239; dead alternative to TOLDI there): frames[n*16] as orc_toldi */
+int orc_shot(const double* xyz, size_t n, double radius, double* frames);
 /* Open3D EstimateNormals(KNN(k)) restatement: normals[n*3], unoriented */
 int orc_normals(const double* xyz, size_t n, int k, double* normals);
 /* GICP covariance from normals (reference .cpp:4-14,45-51): cov[n*9] row-major */

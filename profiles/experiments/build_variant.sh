@@ -11,7 +11,7 @@ TMP=$(mktemp -d)
 mkdir -p "$OUT"
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in spatial_index se3_index knn_features nn_search optimise nccl_dyn capi eval; do
+for f in spatial_index se3_index knn_features shot_lrf nn_search optimise nccl_dyn capi eval; do
   $NVCC $ARCH -O3 -std=c++17 -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr \
      $FLAGS -c $SRC/$f.cu -o $TMP/$f.o 2> $TMP/$f.log &
 done

@@ -17,6 +17,7 @@ if os.environ.get("SE3ICP_LIB"):
 PT2PT, PT2PL, GICP = 0, 1, 2
 RUN_ICP, RUN_SE3_ICP, RUN_SE3_ICP_CF, RUN_SE3_PURE = 0, 1, 2, 3
 NN_AUTO, NN_BRUTE_F32, NN_EXACT_F64, NN_TREE = 0, 1, 2, 3
+LRF_TOLDI, LRF_SHOT = 0, 1
 SOURCE, TARGET = 0, 1
 STAGE_NN_SE3, STAGE_NN_XYZ, STAGE_REDUCE, STAGE_KNN_TARGET = 0, 1, 2, 3
 VARIANTS = {"pt2pt": PT2PT, "pt2pl": PT2PL, "gicp": GICP}
@@ -54,6 +55,9 @@ class Params(C.Structure):
         ("record_history", C.c_int32),
         ("nn_coherence", C.c_int32),
         ("reuse_features", C.c_int32),
+        ("lrf_method", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("lrf_radius", C.c_double),
     ]
 
 
@@ -81,7 +85,7 @@ EXPORTED_SYMBOLS = [
     "se3icp_synchronize", "se3icp_set_cloud", "se3icp_set_cloud_device", "se3icp_run", "se3icp_run_async",
     "se3icp_run_finish", "se3icp_get_history", "se3icp_get_correspondences", "se3icp_get_se3_cloud",
     "se3icp_run_batch", "se3icp_run_batch_device", "se3icp_swap_clouds", "se3icp_run_sequence", "se3icp_run_sharded", "se3icp_comm_unique_id", "se3icp_comm_init",
-    "se3icp_comm_destroy", "se3icp_comm_info", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf",
+    "se3icp_comm_destroy", "se3icp_comm_info", "se3icp_time_stage", "se3icp_knn", "se3icp_lrf", "se3icp_shot_lrf",
     "se3icp_normals", "se3icp_gicp_cov", "se3icp_nn_se3", "se3icp_nn_xyz", "se3icp_trim", "se3icp_reduce_pt2pt",
     "se3icp_reduce_pt2pl", "se3icp_reduce_gicp", "se3icp_solve",
     "se3icp_eval_error_filterreg", "se3icp_eval_corrs_with_gt", "se3icp_eval_lrf_quality", "se3icp_random_downsample",
@@ -334,6 +338,15 @@ class Context:
         fr = np.zeros((n, 4, 4))
         _check(lib().se3icp_lrf(self._h, _dp(xyz), C.c_size_t(n), int(k), _dp(fr)))
         return fr
+
+    def shot_lrf(self, xyz, radius, return_unresolved=False):
+        """SHOT frames with radius support (reference .cpp:121-239): n x 4x4 [x y z p]"""
+        xyz = _f64(xyz)
+        n = xyz.shape[0]
+        fr = np.zeros((n, 4, 4))
+        unresolved = C.c_int64(0)
+        _check(lib().se3icp_shot_lrf(self._h, _dp(xyz), C.c_size_t(n), C.c_double(radius), _dp(fr), C.byref(unresolved)))
+        return (fr, int(unresolved.value)) if return_unresolved else fr
 
     def normals(self, xyz, k):
         xyz = _f64(xyz)

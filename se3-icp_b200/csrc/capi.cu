@@ -389,7 +389,8 @@ int enqueue_setup(se3icp_ctx* c) {
 
     for (int w = 0; w < 2; w++) {
         FeatureArgs fa{};
-        fa.k_lrf = cfg.has_se3 ? p.number_of_nn_for_LRF : 0;
+        const bool shot = cfg.has_se3 && p.lrf_method == SE3ICP_LRF_SHOT;
+        fa.k_lrf = cfg.has_se3 && !shot ? p.number_of_nn_for_LRF : 0;
         if (cfg.variant == SE3ICP_GICP)
             fa.k_nrm = p.knn_normals_gicp;  // .cpp:43 both clouds
         else if (cfg.variant == SE3ICP_PT2PL && w == 1)
@@ -400,6 +401,11 @@ int enqueue_setup(se3icp_ctx* c) {
         fa.nrm = c->nrm[w].as<double>();
         fa.cov = c->cov[w].as<double>();
         fa.K = std::max(fa.k_lrf, fa.k_nrm);
+        if (shot) {  // .cpp:593-594 (commented there): radius-support frames instead of the kNN ones; never reused
+            c->feat[w].valid = false;
+            SE3_TRY(launch_shot_lrf(c->index[w].view, p.lrf_radius, c->frame[w].as<double>(), nullptr, st));
+            c->launches += 1;
+        }
         fa.q_begin = 0;
         fa.q_end = 0x7fffffff;
         if (w == 0 && c->sharded) {  // source features are only needed for this rank's query range
@@ -423,7 +429,7 @@ int enqueue_setup(se3icp_ctx* c) {
             fa.active_count = c->knn_count.as<int>();
         }
         se3icp_ctx::FeatureKey key;
-        key.valid = !(w == 0 && c->sharded);  // a sharded source only holds its own range
+        key.valid = !(w == 0 && c->sharded) && !shot;  // a sharded source only holds its own range; SHOT frames depend on the pair's scale
         key.n = c->n[w];
         key.k_lrf = fa.k_lrf, key.k_nrm = fa.k_nrm, key.want_cov = fa.want_cov, key.eps = fa.gicp_eps;
         const se3icp_ctx::FeatureKey& have = c->feat[w];
@@ -685,6 +691,9 @@ void se3icp_default_params(se3icp_params* p) {  // reference ctor .cpp:334-348
     p->record_history = 0;
     p->nn_coherence = 1;
     p->reuse_features = 1;
+    p->lrf_method = SE3ICP_LRF_TOLDI;
+    p->reserved0 = 0;
+    p->lrf_radius = 0.8;
 }
 
 int se3icp_create(int device, void* stream, se3icp_ctx** out) {
@@ -832,6 +841,20 @@ static int run_async_impl(se3icp_ctx* c, const se3icp_params* p) {
         p->knn_normals_pt2pl > SE3ICP_MAX_KNN) {
         set_last_error("kNN sizes above %d are not supported", SE3ICP_MAX_KNN);
         return SE3ICP_ERR_UNSUPPORTED;
+    }
+    if (p->lrf_method != SE3ICP_LRF_TOLDI && p->lrf_method != SE3ICP_LRF_SHOT) {
+        set_last_error("bad lrf_method %d", p->lrf_method);
+        return SE3ICP_ERR_ARG;
+    }
+    if (p->lrf_method == SE3ICP_LRF_SHOT && p->entry != SE3ICP_RUN_ICP) {
+        if (!(p->lrf_radius > 0.0)) {
+            set_last_error("SHOT frame: lrf_radius must be positive");
+            return SE3ICP_ERR_ARG;
+        }
+        if (c->sharded) {
+            set_last_error("the sharded pair computes TOLDI frames only");
+            return SE3ICP_ERR_UNSUPPORTED;
+        }
     }
     if (p->nn_mode < SE3ICP_NN_AUTO || p->nn_mode > SE3ICP_NN_TREE) {
         set_last_error("bad nn_mode %d", p->nn_mode);
@@ -1376,6 +1399,33 @@ int se3icp_lrf(se3icp_ctx* c, const double* xyz, size_t n, int k, double* frames
     SE3_TRY(stage_features(c, xyz, n, k, 0, k, false));
     std::vector<double> rows(9 * n);
     SE3_TRY(download_planes(c, c->frame[0], rows.data(), n, 9));
+    for (size_t i = 0; i < n; i++) {
+        double* F = frames + 16 * i;
+        const double* r = &rows[9 * i];  // x-axis, y-axis, z-axis
+        for (int col = 0; col < 3; col++)
+            for (int row = 0; row < 3; row++) F[4 * row + col] = r[3 * col + row];
+        F[3] = xyz[3 * i], F[7] = xyz[3 * i + 1], F[11] = xyz[3 * i + 2];
+        F[12] = F[13] = F[14] = 0.0;
+        F[15] = 1.0;
+    }
+    return SE3ICP_OK;
+}
+
+int se3icp_shot_lrf(se3icp_ctx* c, const double* xyz, size_t n, double radius, double* frames, int64_t* unresolved_ties) {
+    SE3_TRY(check_ctx(c));
+    SE3_NOT_PENDING("stage entry point");
+    StageScope stage_scope{c};
+    if (!xyz || !frames || n == 0 || !(radius > 0.0)) return SE3ICP_ERR_ARG;
+    SE3_TRY(upload_cloud_and_index(c, 0, xyz, n));
+    SE3_TRY(c->frame[0].ensure(9 * n * sizeof(double)));
+    SE3_TRY(c->knn_count.ensure(sizeof(int)));
+    SE3_CUDA(cudaMemsetAsync(c->knn_count.ptr, 0, sizeof(int), c->stream));
+    SE3_TRY(launch_shot_lrf(c->index[0].view, radius, c->frame[0].as<double>(), c->knn_count.as<int>(), c->stream));
+    int unresolved = 0;
+    SE3_CUDA(cudaMemcpyAsync(&unresolved, c->knn_count.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> rows(9 * n);
+    SE3_TRY(download_planes(c, c->frame[0], rows.data(), n, 9));  // synchronises the stream
+    if (unresolved_ties) *unresolved_ties = unresolved;
     for (size_t i = 0; i < n; i++) {
         double* F = frames + 16 * i;
         const double* r = &rows[9 * i];  // x-axis, y-axis, z-axis

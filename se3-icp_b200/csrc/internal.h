@@ -196,6 +196,8 @@ struct FeatureArgs {
     int* active_count;
 };
 int launch_knn_features(const CloudIndex& I, const FeatureArgs& fa, cudaStream_t st);
+// shot_lrf.cu: frame planes [9][n] as the feature pass writes them; *unresolved counts median votes that could not be decided
+int launch_shot_lrf(const CloudIndex& I, double radius, double* frame, int* unresolved, cudaStream_t st);
 int launch_cov_from_normals(const double* nrm /*[3][n]*/, int n, double eps, double* cov /*[6][n]*/, cudaStream_t st);
 
 // nn_search.cu

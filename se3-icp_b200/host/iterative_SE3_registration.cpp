@@ -150,6 +150,7 @@ IterativeSE3Registration& IterativeSE3Registration::operator=(const IterativeSE3
     current_correspondences_set_pcl.reset(new pcl::Correspondences(*o.current_correspondences_set_pcl));
     mirror_state_ = o.mirror_state_;
     trim_keep_largest_ = o.trim_keep_largest_;
+    use_shot_lrf_ = o.use_shot_lrf_;
     set_device(o.device_);  // the GPU context is not shared: this object acquires its own on first use
     return *this;
 }
@@ -303,6 +304,8 @@ void IterativeSE3Registration::run_entry(int entry, const std::string& variant_n
     p.beta_transl = beta_transl;
     p.scale_preprocessing = scale_preprocessing;
     p.record_history = entry == SE3ICP_RUN_ICP;
+    p.lrf_method = use_shot_lrf_ ? SE3ICP_LRF_SHOT : SE3ICP_LRF_TOLDI;
+    p.lrf_radius = lrf_radius_;
 
     double T[16];
     se3icp_stats st;

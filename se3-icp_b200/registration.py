@@ -20,7 +20,7 @@ class IterativeSE3Registration:
         self.num_iterations_ = 0
         self.num_pure_se3_iterations_ = -1
         self.mse_ = 0.00001
-        self.lrf_radius_ = 0.8  # only used by the (dead) SHOT frame of the reference
+        self.lrf_radius_ = 0.8  # SHOT frame radius; used only when use_shot_lrf_ is set (reference: dormant, .cpp:593-594)
         self.mse_switch_error_ = 0.001
         self.number_of_nn_for_LRF_ = 30
         self.estimated_overlap_ = 1.0
@@ -34,6 +34,7 @@ class IterativeSE3Registration:
         # extensions (not in the reference): comparator direction of the trimmed rejector and NN strategy
         self.trim_keep_largest_ = True  # PCL 1.14's comparator (include/se3icp.h)
         self.nn_mode_ = capi.NN_AUTO
+        self.use_shot_lrf_ = False  # True: SHOT frames (reference .cpp:121-239) instead of TOLDI
         self._source = np.zeros((0, 3))
         self._target = np.zeros((0, 3))
         self._ctx = capi.Context(device, stream)
@@ -52,7 +53,8 @@ class IterativeSE3Registration:
             max_num_se3_iterations=self.max_num_se3_iterations_, number_of_nn_for_LRF=self.number_of_nn_for_LRF_,
             trim_keep_largest=int(self.trim_keep_largest_), mse=self.mse_, mse_switch_error=self.mse_switch_error_,
             estimated_overlap=self.estimated_overlap_, alpha_rot=self.alpha_rot, beta_transl=self.beta_transl,
-            scale_preprocessing=self.scale_preprocessing, nn_mode=self.nn_mode_, record_history=int(entry == capi.RUN_ICP))
+            scale_preprocessing=self.scale_preprocessing, nn_mode=self.nn_mode_, record_history=int(entry == capi.RUN_ICP),
+            lrf_method=int(self.use_shot_lrf_), lrf_radius=self.lrf_radius_)
 
     def _run(self, entry, variant_name):
         if variant_name not in capi.VARIANTS:

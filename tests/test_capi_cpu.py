@@ -22,7 +22,7 @@ def test_header_symbols_exported(capi):
     for n in names:
         assert hasattr(lib, n), "libse3icp_cuda.so does not export %s" % n
     assert sorted(capi.EXPORTED_SYMBOLS) == names
-    assert lib.se3icp_abi_version() == 3
+    assert lib.se3icp_abi_version() == 4
 
 
 def test_default_params_match_reference_ctor(capi):
@@ -31,13 +31,16 @@ def test_default_params_match_reference_ctor(capi):
     assert (p.mse, p.mse_switch_error, p.estimated_overlap) == (1e-5, 1e-3, 1.0)
     assert (p.alpha_rot, p.beta_transl, p.scale_preprocessing) == (3.0, 1.0, 3.0)
     assert (p.knn_normals_pt2pl, p.knn_normals_gicp, p.gicp_epsilon) == (30, 20, 1e-3)
+    assert (p.lrf_method, p.lrf_radius) == (capi.LRF_TOLDI, 0.8)  # .cpp:340; TOLDI is the reference's active frame
 
 
 def test_params_layout_matches_oracle(capi, orc):
-    """the shared prefix of se3icp_params and orc_params has identical field order and types"""
-    a = [(n, t) for n, t in capi.Params._fields_][:15]
+    """the algorithmic fields of se3icp_params and orc_params have identical order and types: the reference's 15, then
+    the execution switches that exist only on the CUDA side, then the frame choice both sides share"""
+    a = [(n, t) for n, t in capi.Params._fields_]
     b = [(n, t) for n, t in orc.Params._fields_]
-    assert a == b
+    assert a[:15] == b[:15]
+    assert a[-3:] == b[-3:] and [n for n, _ in b[-3:]] == ["lrf_method", "reserved0", "lrf_radius"]
 
 
 def test_no_cpu_fallback(capi):
