@@ -6,4 +6,5 @@ capi.py        ctypes binding of the C ABI
 registration.py  Python mirror of IterativeSE3Registration (same names / defaults / error behaviour)
 """
 from . import capi, sharding  # noqa: F401
-from .registration import IterativeSE3Registration, run_registration_method, register_sequence, METHODS  # noqa: F401
+from .registration import (IterativeSE3Registration, run_registration_method, register_sequence, METHODS,  # noqa: F401
+                           make_hybrid_alpha_grid, benchmark_different_rot_scales)

@@ -160,3 +160,37 @@ def register_sequence(method, scans, device=0, **params):
         raise ValueError("Not a valid algorithm name; available: %s" % ", ".join(METHODS))
     ctx = capi.Context(device)
     return ctx.run_sequence(list(scans), capi.default_params(variant=variant, entry=entry, **params))
+
+
+def make_hybrid_alpha_grid():
+    """examples/benchmark_kitti.cpp:354-384 (makeHybridLGrid): the rotation-scale values of the reference's alpha sweep —
+    0, 0.01..0.10 step 0.01, 0.2..1.0 step 0.1, 1.0..5.0 step 0.5, then a geometric tail up to 1000; sorted, unique."""
+    grid = [0.0]
+    grid += [i * 0.01 for i in range(1, 11)]
+    grid += [i * 0.1 for i in range(2, 11)]
+    grid += [1.0 + i * 0.5 for i in range(0, 9)]
+    grid += [5, 7, 10, 15, 25, 50, 60, 70, 80, 90, 100, 200, 300, 400, 500, 600, 700, 800, 900, 1000]
+    return sorted(set(float(a) for a in grid))
+
+
+def benchmark_different_rot_scales(method, source, target, alphas=None, device=0, **params):
+    """The reference's alpha-sweep harness (examples/benchmark_kitti.cpp:387-393, benchmark_different_rot_scales) for one
+    pair: the same registration once per rotation scale alpha_rot.  The frames, normals and covariances of a cloud do not
+    depend on alpha, so they are computed for the first value only and reused by the others (params.reuse_features; the
+    12-D rows and their search structure are rebuilt per value).  Returns [(alpha, T 4x4, Stats)]."""
+    if method in ("se3_pt2pt", "se3_pt2pl", "se3_gicp"):
+        entry, variant = capi.RUN_SE3_ICP, method[4:]
+    elif method == "se3_gicp_with_cf":
+        entry, variant = capi.RUN_SE3_ICP_CF, "gicp"
+    else:
+        raise ValueError("the rotation scale only enters the SE(3) methods; available: %s" % ", ".join(METHODS[3:]))
+    ctx = capi.Context(device)
+    ctx.set_cloud(capi.SOURCE, source)
+    ctx.set_cloud(capi.TARGET, target)
+    out = []
+    for alpha in (make_hybrid_alpha_grid() if alphas is None else alphas):
+        p = capi.default_params(variant=variant, entry=entry, reuse_features=1, **dict(params, alpha_rot=float(alpha)))
+        T, st = ctx.run(p)
+        out.append((float(alpha), T, st))
+    ctx.close()
+    return out

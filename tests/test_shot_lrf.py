@@ -207,3 +207,29 @@ def test_cuda_shot_frames_are_never_reused_and_differ_from_toldi(ctx, capi, pkg)
     np.testing.assert_array_equal(reg.current_estimated_T_, T1)
     with pytest.raises(Exception):
         ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, lrf_method=capi.LRF_SHOT, lrf_radius=0.0))
+
+
+# ---------------------------------------------------------------------------------------------- alpha-sweep harness
+def test_alpha_grid_matches_the_reference_harness(pkg):
+    """examples/benchmark_kitti.cpp:354-384: 0, the three linear ranges and the tail, sorted and unique"""
+    g = pkg.make_hybrid_alpha_grid()
+    assert g == sorted(set(g)) and g[0] == 0.0 and g[-1] == 1000.0
+    assert len(g) == 1 + 10 + 9 + 9 + 20 - 2  # 1.0 and 5.0 appear twice in the reference's lists
+    for v in (0.01, 0.1, 0.2, 1.0, 1.5, 5.0, 7.0, 100.0):
+        assert any(abs(a - v) < 1e-12 for a in g)
+
+
+@pytest.mark.gpu
+def test_alpha_sweep_reuses_features_and_matches_oracle(pkg, capi):
+    """.cpp:387-393 on the fixture: every rotation scale of a short grid (incl. alpha = 0: position-only lifting, and a
+    very large one) gives the oracle's transform and iteration counts; the kNN / frame stage runs once per cloud"""
+    src, tgt, _ = W.load_c1()
+    alphas = [0.0, 0.05, 1.0, 3.0, 50.0, 1000.0]
+    res = pkg.benchmark_different_rot_scales("se3_pt2pl", src, tgt, alphas=alphas, number_of_nn_for_LRF=90, **RRM)
+    assert [a for a, _, _ in res] == alphas
+    assert [st.feature_reuses for _, _, st in res] == [0] + [2] * (len(alphas) - 1)
+    for alpha, T, st in res:
+        po = orc.default_params(variant="pt2pl", entry=orc.RUN_SE3_ICP, alpha_rot=alpha, number_of_nn_for_LRF=90, **RRM)
+        To, so, _ = orc.run(src, tgt, po)
+        assert (st.num_iterations, st.num_pure_se3_iterations) == (so.num_iterations, so.num_pure_se3_iterations), alpha
+        assert W.rotation_error(T, To) < 1e-5 and np.abs(T[:3, 3] - To[:3, 3]).max() < 1e-5, alpha
