@@ -21,6 +21,13 @@
 
 namespace se3 {
 
+#if NN_COUNT_VISITS  // development build only (profiles/experiments): how many boxes / leaves the 12-D search opens
+__device__ unsigned long long g_nn_visits[4];  // queries, node tests (32 boxes each), leaves evaluated, exact rows
+#define NN_COUNT(slot, v) do { const unsigned long long v__ = (unsigned long long)(v); if (lane == 0) atomicAdd(&g_nn_visits[slot], v__); } while (0)
+#else
+#define NN_COUNT(slot, v) do { } while (0)
+#endif
+
 __device__ __forceinline__ bool se3_phase_active(const RunConfig& cfg, const IterState* st) {
     return cfg.has_se3 && (cfg.pure || !st->switch_icp);
 }
@@ -434,6 +441,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     const size_t m = (size_t)M, tn = (size_t)T.idx.total_nodes;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
+    NN_COUNT(0, 1);
     double* q = qs[wib];  // the FP64 query lives in shared memory; only its FP32 image stays in registers
     {
         double qr[12];
@@ -462,6 +470,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     float qk1, qk2;
     rounding_correction(__fmul_ru(7.f, qeps), qk1, qk2);  // 7 qeps > 2 sqrt(12) qeps
     auto lb_fn = [&](int node) -> double {
+        NN_COUNT(1, 1);
         const float4* b = reinterpret_cast<const float4*>(T.box12) + node;
         float acc = 0.f;
 #pragma unroll
@@ -494,6 +503,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
     int skip_leaf = -1;
     auto leaf_fn = [&](int leaf) {
         if (leaf == skip_leaf) return;
+        NN_COUNT(2, 1);
         int p = leaf * 32 + lane;
         bool cand = false;
         if (p < M) {
@@ -515,6 +525,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
             cand = (double)(d32 - eps) <= (coherent ? b2 : tau);
         }
         if (__ballot_sync(SE3_FULL, cand) == 0u) return;
+        NN_COUNT(3, __popc(__ballot_sync(SE3_FULL, cand)));
         double d2 = inf;
         int id = 0x7fffffff;
         if (cand) {
@@ -702,6 +713,18 @@ static int launch_nn_search_which(const SourceView& S, const TargetView& T, cons
     SE3_CUDA(cudaGetLastError());
     return 0;
 }
+
+#if NN_COUNT_VISITS
+extern "C" int se3icp_debug_nn_visits(unsigned long long out[4], int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_nn_visits, sizeof(g_nn_visits));
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_nn_visits, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int launch_nn_search(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                      cudaStream_t st) {
