@@ -781,19 +781,20 @@ __device__ __noinline__ void solve_update_block(const RunConfig& cfg, IterState*
     __shared__ double wsum[8][kReducePartials];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;  // 4 or 8 warps
     {   // fixed-order sum of the per-block records: warp w takes records w, w + nw, ...; then the warp sums in order
-        // (eight independent L2 loads in flight, added in the fixed order b = w, w + 8, ...: one dependent load per
-        // addition made this chain 13 us long)
+        // (kTailLoads independent L2 loads in flight, added in the fixed order b = w, w + nw, ...: one dependent load per
+        // addition made this chain 13 us long, eight in flight still took ten round trips for the 296 records)
+        constexpr int kTailLoads = 32;
         double s = 0.0;
         if (lane < kAcc) {
-            for (int b0 = w; b0 < n_records; b0 += 8 * nw) {
-                double v[8];
+            for (int b0 = w; b0 < n_records; b0 += kTailLoads * nw) {
+                double v[kTailLoads];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < kTailLoads; u++) {
                     const int b = b0 + nw * u;
                     v[u] = b < n_records ? __ldcg(&partials[b * kReducePartials + lane]) : 0.0;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++)
+                for (int u = 0; u < kTailLoads; u++)
                     if (b0 + nw * u < n_records) s += v[u];
             }
         }
