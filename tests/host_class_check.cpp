@@ -62,6 +62,24 @@ int main(int argc, char** argv) {
     // and the translation column of a mirrored SE(3) element is beta * the moved point (.cpp:605-607,713-716)
     Eigen::Vector3d t0 = a.source_se3_cloud_[0].block<3, 1>(0, 3);
     if ((t0 - a.source_moving_.points_[0] * a.beta_transl).norm() > 1e-9) return fail("source_se3_cloud_ inconsistent with source_moving_");
-    std::printf("HOST_CLASS_CHECK OK (%zu points, %d iterations, worst matched distance %.2e)\n", n, a.num_iterations_, worst);
+    // SHOT frames (reference .cpp:121-239, its calls commented out at .cpp:593-594): the switch reaches the CUDA path
+    // (other frames: a different number of SE(3) iterations on this fixture is allowed, the same answer is not), survives
+    // a copy, and the registration still lands on the ground truth of the exact-copy fixture, like the TOLDI run above
+    IterativeSE3Registration s;
+    s.setSourceCloud(std::string(argv[1]));
+    s.setTargetCloud(std::string(argv[2]));
+    s.max_num_se3_iterations_ = 10;
+    s.mse_switch_error_ = 5e-5;
+    s.lrf_radius_ = 0.8;
+    s.set_use_shot_lrf(true);
+    IterativeSE3Registration s2(s);
+    s.run_se3_icp("pt2pl");
+    s2.run_se3_icp("pt2pl");
+    if ((s.current_estimated_T_ - s2.current_estimated_T_).norm() != 0.0) return fail("the copy lost the SHOT switch");
+    if ((s.current_estimated_T_ - a.current_estimated_T_).norm() > 1e-6) return fail("SHOT-frame registration missed the ground truth");
+    if ((s.current_estimated_T_ - a.current_estimated_T_).norm() == 0.0 && s.num_pure_se3_iterations_ == a.num_pure_se3_iterations_)
+        std::printf("note: SHOT and TOLDI runs coincide bit for bit\n");
+    std::printf("HOST_CLASS_CHECK OK (%zu points, %d iterations, worst matched distance %.2e; SHOT frames: %d iterations)\n", n,
+                a.num_iterations_, worst, s.num_iterations_);
     return 0;
 }
