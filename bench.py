@@ -18,7 +18,8 @@ independent pairs (32 -> 256 pairs at 8 GPUs, the named configuration); no data-
             only; the reference's own source, compiled against stand-in Open3D/PCL/Eigen (oracle/_ref), is 3-4x slower
             than the port and is reported next to it, not as the baseline
   configs   (N = 1) every other single-GPU configuration of BASELINE.json through the same C ABI — configs[0] fixture,
-            configs[1] bunny x 3 difficulty levels x 3 variants, configs[3] lounge-like with_cf — each with its device
+            configs[1] bunny x 3 difficulty levels x 3 variants, configs[3] lounge-like with_cf, and the SHOT frame of
+            SURVEY 8f rank 4 — each with its device
             time and its parity against the CPU oracle on the same input (rotation / translation difference, iteration
             counts).  Parity lines, not bench values.
   sharded_pair  (N > 1) BASELINE.json configs[4]: ONE ~10 M-point pair, se3_pt2pl, through se3icp_run_sharded with the
@@ -274,6 +275,31 @@ def configs_block(capi, orc, device):
                 "registrations_per_s": len(batch) / dt, "wall_ms": 1e3 * dt,
                 "iterations": [int(s.num_iterations) for s in st[:4]],
                 "max_rot_err_vs_gt_rad": max(W.rotation_error(T[k], frames[k % 4][2]) for k in range(8))})
+    # the SHOT frame the reference keeps beside TOLDI (.cpp:121-239; calls commented out at .cpp:593-594)
+    pts = W.load_bunny().astype(np.float64)
+    pts = (pts - pts.mean(0)) * (3.0 / np.linalg.norm(pts - pts.mean(0), axis=1).max())  # the scale the class works at
+    with capi.Context(device) as ctx:
+        ctx.shot_lrf(pts, 0.8)
+        t0 = time.perf_counter()
+        fg, unresolved = ctx.shot_lrf(pts, 0.8, return_unresolved=True)
+        gpu_ms = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        fo = orc.shot(pts, 0.8)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        out.append({"config": "8f rank 4: SHOT frames (se3icp_shot_lrf) of the full bunny, radius 0.8 (lrf_radius_, .cpp:340), host buffers",
+                    "points": [len(pts)], "gpu_wall_ms": gpu_ms, "oracle_cpu_ms": cpu_ms,
+                    "max_abs_diff_vs_oracle": float(np.abs(fg - fo).max()), "unresolved_median_votes": int(unresolved)})
+        src, tgt, T_gt = W.load_c1()
+        ctx.set_cloud(capi.SOURCE, src)
+        ctx.set_cloud(capi.TARGET, tgt)
+        kw = dict(estimated_overlap=1.0, max_num_se3_iterations=10, mse=1e-5, mse_switch_error=5e-5)
+        T, st = ctx.run(capi.default_params(variant="pt2pl", entry=capi.RUN_SE3_ICP, lrf_method=capi.LRF_SHOT, lrf_radius=0.8, **kw))
+        To, so, _ = orc.run(src, tgt, orc.default_params(variant="pt2pl", entry=orc.RUN_SE3_ICP, lrf_method=1, lrf_radius=0.8, **kw))
+        out.append({"config": "8f rank 4: fixture se3_pt2pl on SHOT frames (lrf_method = SHOT)", "points": [len(src), len(tgt)],
+                    "gpu_ms": float(st.time_total_ms), "iterations": [int(st.num_iterations), int(st.num_pure_se3_iterations)],
+                    "iterations_equal": bool(st.num_iterations == so.num_iterations and
+                                             st.num_pure_se3_iterations == so.num_pure_se3_iterations),
+                    "rot_vs_oracle_rad": W.rotation_error(T, To), "rot_vs_gt_rad": W.rotation_error(T, T_gt)})
     return out
 
 
