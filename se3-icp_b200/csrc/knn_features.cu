@@ -23,6 +23,13 @@ constexpr int kPool = 256;  // unsorted candidate pool per warp
 #define KNN_QPW 1
 #endif
 constexpr int kQpw = KNN_QPW;  // queries per warp between two block barriers
+#ifndef KNN_SLACK
+#define KNN_SLACK 12
+#endif
+// a pool shrink accepts any radius that keeps K .. K + kSlack candidates: the interpolated count search hits a narrow
+// window in as few rounds as a wide one, and fewer survivors mean a tighter radius (per 119 k-point cloud, K = 90:
+// kSlack 4 / 8 / 12 / 16 / 24 / 32 / 38 -> 0.829 / 0.826 / 0.828 / 0.830 / 0.836 / 0.845 / 0.852 ms)
+constexpr int kSlack = KNN_SLACK;
 
 struct KnnScratch {
     unsigned long long d[kPool];
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         int Li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
         // Search phase: candidates within the current radius go to an UNSORTED pool in shared memory.  When the
         // pool fills up, a search on the distance value (compares + one integer warp reduction per step, no data
-        // movement) finds a radius that keeps between K and K+24 of them and the pool is compacted.  Sorting happens
+        // movement) finds a radius that keeps between K and K + kSlack of them and the pool is compacted.  Sorting happens
         // once, at the end, on the ~K survivors.
         int pool = 0;
         double tau = inf;
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
             return r;
         };
         auto shrink_pool = [&]() {
-            if (pool <= K + 24) return;
+            if (pool <= K + kSlack) return;
             double e[8];
             int eid[8];
             // Bounds of the search need not be tight: 0 below, the current radius above (every pool entry passed
@@ -189,14 +196,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
             double lo = 0.0, hi = tau;
             if (!(tau < inf)) hi = __hiloint2double((int)(__reduce_max_sync(SE3_FULL, hmax) + 1u), 0);
             // Squared distances of points on a surface are spread almost uniformly, so interpolating the count (regula
-            // falsi on the empirical distribution, aimed at the middle of the accepted window K .. K + 24) needs 2-3
+            // falsi on the empirical distribution, aimed at the middle of the accepted window K .. K + kSlack) needs 2-3
             // rounds where halving the interval needs 6-8; every other round from the fourth on halves, which bounds
             // the worst case.  count(d <= hi) >= K holds throughout.
             int c_lo = 0, c_hi = pool;
             for (int it = 0; it < 24; it++) {
                 double mid;
                 if (it < 3 || (it & 1)) {
-                    const float f = __fdividef((float)(K + 12 - c_lo), (float)(c_hi - c_lo));
+                    const float f = __fdividef((float)(K + kSlack / 2 - c_lo), (float)(c_hi - c_lo));
                     mid = fma(hi - lo, (double)f, lo);
                 } else {
                     mid = 0.5 * (lo + hi);
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
                 } else {
                     hi = mid;
                     c_hi = c;
-                    if (c <= K + 24) break;
+                    if (c <= K + kSlack) break;
                 }
             }
             __syncwarp();
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
             pool = out;
             tau = hi;
             __syncwarp();
-            if (pool > K + 24) {  // ties at the threshold (pool >= K holds, so the K-th entry exists)
+            if (pool > K + kSlack) {  // ties at the threshold (pool >= K holds, so the K-th entry exists)
                 tau = exact_trim(pool, K);
                 pool = K;
             }
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
         if (active) {
             for (int leaf = w0; leaf <= w1; leaf++) eval_leaf(leaf);
             shrink_pool();
-            if (pool >= K && !(tau < inf)) {  // K .. K + 24 seeds: nothing to shrink, but they do bound the radius
+            if (pool >= K && !(tau < inf)) {  // K .. K + kSlack seeds: nothing to shrink, but they do bound the radius
                 unsigned hmax = 0u;
                 for (int t = lane; t < pool; t += 32) hmax = max(hmax, (unsigned)(W.d[t] >> 32));
                 tau = __hiloint2double((int)(__reduce_max_sync(SE3_FULL, hmax) + 1u), 0);
@@ -285,9 +292,9 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIn
                 eval_leaf(leaf);
             });
             shrink_pool();
-            // exact order of the survivors (K .. K + 24 of them): the list is striped over the warp, element e in lane
+            // exact order of the survivors (K .. K + kSlack of them): the list is striped over the warp, element e in lane
             // e % 32, register e / 32
-            if (pool > 128) {  // K + 24 > 128: cut to exactly K first
+            if (pool > 128) {  // K + kSlack > 128: cut to exactly K first
                 tau = exact_trim(pool, K);
                 pool = K;
             }
