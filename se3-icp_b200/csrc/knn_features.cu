@@ -14,7 +14,13 @@
 
 namespace se3 {
 
-constexpr int kKnnWarps = 16;  // 16 warps x 2 blocks per SM at 64 registers: 1.02 ms per 119 k-point cloud (12 x 2 at 80 registers 1.10, 32 x 1 1.05,
+#ifndef KNN_WARPS
+#define KNN_WARPS 16
+#endif
+#ifndef KNN_BLOCKS
+#define KNN_BLOCKS 2
+#endif
+constexpr int kKnnWarps = KNN_WARPS;  // 16 warps x 2 blocks per SM at 64 registers: 1.02 ms per 119 k-point cloud (12 x 2 at 80 registers 1.10, 32 x 1 1.05,
                                // 8 x 4 1.13, 24 x 1 at 80 registers 1.11): neighbouring queries share L1 lines, and 32 warps per SM hide the
                                // latency of the serial selection loops better than 24 do, spills included
 constexpr int kPool = 256;  // unsorted candidate pool per warp
@@ -98,7 +104,7 @@ __device__ __forceinline__ bool sort_pool_quantised(const unsigned long long* pd
     return __ballot_sync(SE3_FULL, tie) == 0u;
 }
 
-__global__ void __launch_bounds__(kKnnWarps * 32, 2) knn_features_kernel(CloudIndex I, FeatureArgs fa) {
+__global__ void __launch_bounds__(kKnnWarps * 32, KNN_BLOCKS) knn_features_kernel(CloudIndex I, FeatureArgs fa) {
     extern __shared__ __align__(16) unsigned char knn_smem[];  // dynamic: more than 48 KB from 12 warps per block on
     KnnScratch* scratch = reinterpret_cast<KnnScratch*>(knn_smem);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
