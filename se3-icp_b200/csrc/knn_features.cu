@@ -20,15 +20,17 @@ namespace se3 {
 #ifndef KNN_BLOCKS
 #define KNN_BLOCKS 2
 #endif
-constexpr int kKnnWarps = KNN_WARPS;  // 16 warps x 2 blocks per SM at 64 registers: 1.02 ms per 119 k-point cloud (12 x 2 at 80 registers 1.10, 32 x 1 1.05,
-                               // 8 x 4 1.13, 24 x 1 at 80 registers 1.11): neighbouring queries share L1 lines, and 32 warps per SM hide the
-                               // latency of the serial selection loops better than 24 do, spills included
+// 16 warps x 2 blocks per SM at 64 registers: neighbouring queries share L1 lines, and 32 warps per SM hide the latency of
+// the serial selection loops better than 24 do, spills included.  Per 119 k-point cloud: 0.826 ms against 12 x 2 (80
+// registers) 0.876, 8 x 4 0.880, 10 x 3 0.882, 20 x 1 0.956 (re-swept at the end of round 2; same ranking as before the
+// kernel changes of that round).  The macros exist for such sweeps (profiles/experiments/build_variant.sh).
+constexpr int kKnnWarps = KNN_WARPS;
 constexpr int kPool = 256;  // unsorted candidate pool per warp
 
 #ifndef KNN_QPW
 #define KNN_QPW 1
 #endif
-constexpr int kQpw = KNN_QPW;  // queries per warp between two block barriers
+constexpr int kQpw = KNN_QPW;  // queries per warp between two block barriers (2 / 3: 1.01 / 1.15 ms against 0.885 ms for 1)
 #ifndef KNN_SLACK
 #define KNN_SLACK 12
 #endif
