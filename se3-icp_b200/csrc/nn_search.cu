@@ -332,7 +332,13 @@ __device__ __forceinline__ int seed_position_xyz(const CloudIndex& I, double qx,
 //    possibly far in position); and, while the estimate still moves a lot (||T_prev - T||_F > cfg.reseed_thr), whenever
 //    the seed is closer than the remembered match — measured: with the remembered match alone the second pass of a
 //    KITTI-size pair cost more than the cold first one.  The search is exact from any starting point.
-__global__ void __launch_bounds__(256, 3) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
+#ifndef NN_FILTER_THREADS
+#define NN_FILTER_THREADS 256
+#endif
+#ifndef NN_FILTER_BLOCKS
+#define NN_FILTER_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(NN_FILTER_THREADS, NN_FILTER_BLOCKS) nn_filter_kernel(SourceView S, TargetView T, RunConfig cfg,
                                                          IterState* __restrict__ state, CorrBuffers cb) {
     if (state->done) return;
     const bool se3 = se3_phase_active(cfg, state);
@@ -410,9 +416,9 @@ __global__ void __launch_bounds__(256, 3) nn_filter_kernel(SourceView S, TargetV
 
 int launch_nn_filter(const SourceView& S, const TargetView& T, const RunConfig& cfg, IterState* state, CorrBuffers cb,
                      cudaStream_t st) {
-    int g = (S.end - S.begin + 255) / 256;
+    int g = (S.end - S.begin + NN_FILTER_THREADS - 1) / NN_FILTER_THREADS;
     if (g < 1) g = 1;
-    nn_filter_kernel<<<g, 256, 0, st>>>(S, T, cfg, state, cb);
+    nn_filter_kernel<<<g, NN_FILTER_THREADS, 0, st>>>(S, T, cfg, state, cb);
     SE3_CUDA(cudaGetLastError());
     return 0;
 }
