@@ -332,9 +332,6 @@ __device__ __forceinline__ int seed_position_xyz(const CloudIndex& I, double qx,
 //    possibly far in position); and, while the estimate still moves a lot (||T_prev - T||_F > cfg.reseed_thr), whenever
 //    the seed is closer than the remembered match — measured: with the remembered match alone the second pass of a
 //    KITTI-size pair cost more than the cold first one.  The search is exact from any starting point.
-#ifndef NN_PREFETCH
-#define NN_PREFETCH 0  // bit 0: leaf rows, bit 1: child boxes of the entry a 1-NN traversal opens after the current one
-#endif
 #ifndef NN_FILTER_THREADS
 #define NN_FILTER_THREADS 256
 #endif
@@ -584,28 +581,7 @@ __device__ __forceinline__ void se3_tree_body(const SourceView& S, const TargetV
         skip_leaf = first;
     }
     // prune against the second-best bound when it is being tracked
-#if NN_PREFETCH
-    auto pf_fn = [&](int lvl, int node) {
-        if (lvl == 0) {
-            const int p = node * 32 + lane;
-            if (p < M && (NN_PREFETCH & 1)) {
-                prefetch_l1(T.rows32 + p);
-                prefetch_l1(T.rows32 + m + p);
-                prefetch_l1(T.rows32 + 2 * m + p);
-            }
-        } else if (NN_PREFETCH & 2) {
-            const int c = node * 32 + lane;
-            if (c < T.idx.level_cnt[lvl - 1]) {
-                const float4* b = reinterpret_cast<const float4*>(T.box12) + T.idx.level_off[lvl - 1] + c;
-#pragma unroll
-                for (int kk = 0; kk < 6; kk++) prefetch_l1(b + (size_t)kk * tn);
-            }
-        }
-    };
-    traverse_nodes<true, false>(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn, pf_fn);
-#else
     traverse_nodes<true, false>(T.idx, lb_fn, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
-#endif
     if (lane == 0) {
         write_se3_match(T, cfg, cb, i, q, best_j, tau);
         if (cfg.coherence) {  // certificate for later iterations: second-nearest distance + the iteration it belongs to
@@ -695,31 +671,7 @@ __device__ __forceinline__ void xyz_body(const SourceView& S, const TargetView& 
         leaf_fn(first);
         skip_leaf = first;
     }
-#if NN_PREFETCH
-    auto pf_fn = [&](int lvl, int node) {
-        if (lvl == 0) {
-            const int p = node * 32 + lane;
-            if (p < I.n && (NN_PREFETCH & 1)) {
-                prefetch_l1(I.sx + p);
-                prefetch_l1(I.sy + p);
-                prefetch_l1(I.sz + p);
-                prefetch_l1(I.perm + p);
-            }
-        } else if (NN_PREFETCH & 2) {
-            const int c = node * 32 + lane;
-            if (c < I.level_cnt[lvl - 1]) {
-                const float2* b = I.box + I.level_off[lvl - 1] + c;
-                const size_t tn = (size_t)I.total_nodes;
-                prefetch_l1(b);
-                prefetch_l1(b + tn);
-                prefetch_l1(b + 2 * tn);
-            }
-        }
-    };
-    traverse_boxes<true>(I, qx, qy, qz, coherent ? b2 : tau, stacks[wib], lane, leaf_fn, pf_fn);
-#else
     traverse_boxes<true>(I, qx, qy, qz, coherent ? b2 : tau, stacks[wib], lane, leaf_fn);
-#endif
 
     if (lane == 0) {
         double d = sqrt(tau);  // .cpp:411

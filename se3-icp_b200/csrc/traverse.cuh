@@ -4,8 +4,6 @@
 // shrinking search radius when popped.
 #pragma once
 
-#include <type_traits>
-
 #include "common.cuh"
 #include "internal.h"
 
@@ -62,16 +60,10 @@ __device__ __forceinline__ double box_lower_bound(const CloudIndex& I, int node,
 // bound first another 1 %); the 1-NN searches lose 4 % either way (more spills at their 48 registers), so they keep the
 // stack for their leaves — ordering THEIR stack pushes by bound (most promising child on top) opens 3 % fewer leaves and
 // changes a KITTI-size pair by -1 %, a 150-iteration bunny run by +2 %: not kept.
-// pf_fn(level, node): optional, semantically neutral hint that the entry (level, node) is likely to be opened soon (the
-// 1-NN searches issue L1 prefetches for the rows of a leaf / the child boxes of a node; NN_PREFETCH, see nn_search.cu).
-struct NoPrefetch {
-    __device__ __forceinline__ void operator()(int, int) const {}
-};
-template <bool kWideStart, bool kLeafMask, class LbFn, class LeafFn, class PfFn = NoPrefetch>
+template <bool kWideStart, bool kLeafMask, class LbFn, class LeafFn>
 __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn, const double& tau, int2* stack, int lane,
-                                               LeafFn&& leaf_fn, PfFn&& pf_fn = PfFn()) {
+                                               LeafFn&& leaf_fn) {
     const double kSlack = 1.0 - 1e-12;  // never prune on a rounding-level difference
-    constexpr bool kHint = !std::is_same<typename std::decay<PfFn>::type, NoPrefetch>::value;
     int sp = 0;
     {
         // every node of the start level, 32 at a time: the rounds are independent, so their loads overlap
@@ -116,10 +108,6 @@ __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn
             int lvl = e.x >> 27, node = e.x & ((1 << 27) - 1);
             if (lvl == 0) {
                 leaf = node;
-                if (kHint && sp > 0) {  // a leaf pushes nothing: the entry below is the next one popped
-                    const int2 nx = stack[sp - 1];
-                    if ((double)__int_as_float(nx.y) * kSlack <= tau) pf_fn(nx.x >> 27, nx.x & ((1 << 27) - 1));
-                }
             } else {
                 int cl = lvl - 1;
                 int c = node * 32 + lane;
@@ -138,10 +126,6 @@ __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn
                     if (ok) stack[sp + __popc(m & ((1u << lane) - 1u))] = make_int2((cl << 27) | c, __float_as_int(__double2float_rd(lb)));
                     sp += __popc(m);
                     __syncwarp();
-                    if (kHint && __popc(m) >= 2) {  // the top child is opened next anyway; hint the one after it
-                        const int2 nx = stack[sp - 2];
-                        pf_fn(nx.x >> 27, nx.x & ((1 << 27) - 1));
-                    }
                 }
                 continue;
             }
@@ -150,14 +134,11 @@ __device__ __forceinline__ void traverse_nodes(const CloudIndex& I, LbFn&& lb_fn
     }
 }
 
-template <bool kWideStart, class LeafFn, class PfFn = NoPrefetch>
+template <bool kWideStart, class LeafFn>
 __device__ __forceinline__ void traverse_boxes(const CloudIndex& I, double qx, double qy, double qz, const double& tau,
-                                               int2* stack, int lane, LeafFn&& leaf_fn, PfFn&& pf_fn = PfFn()) {
+                                               int2* stack, int lane, LeafFn&& leaf_fn) {
     const BoxQuery bq = make_box_query(qx, qy, qz);
-    traverse_nodes<kWideStart, !kWideStart>(I, [&](int node) { return box_lower_bound(I, node, bq); }, tau, stack, lane, leaf_fn,
-                                            pf_fn);
+    traverse_nodes<kWideStart, !kWideStart>(I, [&](int node) { return box_lower_bound(I, node, bq); }, tau, stack, lane, leaf_fn);
 }
-
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 }  // namespace se3
