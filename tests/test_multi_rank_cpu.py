@@ -94,3 +94,25 @@ def test_world2_gloo(tmp_path):
         np.testing.assert_allclose(r[k]["sum27"], r[k]["whole"], rtol=1e-12, atol=1e-12)
     np.testing.assert_array_equal(r[0]["sum27"], r[1]["sum27"])  # all-reduce: identical bits on every rank
     np.testing.assert_array_equal(r[0]["T"], r[1]["T"])          # hence the identical solve, no broadcast needed
+
+
+def test_reference_arm_under_torchrun_world2():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone times the CPU path and prints
+    ONE JSON line (impl, cpu_baseline, e2e with zero copy bytes); the other rank exits 0 without output."""
+    import json
+    import subprocess
+
+    port = 31500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "registrations/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert abs(d["e2e"]["value"] - d["value"]) < 1e-9 and "BASELINE.json configs[2]" in d["config"]["workload"]
